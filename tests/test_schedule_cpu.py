@@ -1,0 +1,67 @@
+"""The product's kernel schedule (s2m2_b200/model.py) run with the plain-torch op restatement on CPU.
+
+Validates weight packing / fusion / buffer aliasing / op order of the host side against the oracle and
+the reference-generated golden vectors.  The CUDA kernels themselves are checked in the -m gpu tests.
+"""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from oracle import s2m2_oracle as O
+from s2m2_b200.model import S2M2
+from s2m2_b200.weights import random_state_dict, synthetic_pair
+from torch_ops import TorchOps
+
+
+def _build(cfg, precision="fp32"):
+    sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
+    m = S2M2(cfg["C"], 1, cfg["NTR"], use_positivity=cfg["pos"], refine_iter=cfg["it"], precision=precision).eval()
+    m.my_load_state_dict(sd)
+    m.ops = TorchOps()
+    return m, sd
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES[:3])
+def test_schedule_matches_golden(name):
+    cfg, g = load_golden(name)
+    m, sd = _build(cfg)
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    m.taps = {}
+    d, o, c = m(left, right)
+    assert d.shape == (cfg["B"], 1, cfg["H"], cfg["W"]) and d.dtype == torch.float32
+    assert (m.taps["disp_init.cv"] - g["tap:disp_init#0.3"]).abs().max() < 2e-3
+    assert (m.taps["disp_init.disp"] - g["tap:disp_init#0.0"]).abs().max() < 1e-3
+    assert (d - g["disp"]).abs().max() < 2e-3
+    assert (d - g["disp"]).abs().mean() < 5e-5
+    assert (o - g["occ"]).abs().max() < 1e-4
+    assert (c - g["conf"]).abs().max() < 1e-4
+
+
+def test_schedule_stage_taps_match_oracle():
+    cfg, g = load_golden("tiny_c32_64x96")
+    m, sd = _build(cfg)
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    m.taps = {}
+    m(left, right)
+    ot = {}
+    O.forward(sd, left, right, cfg["NTR"], cfg["pos"], cfg["it"], ot)
+    for k in ("cnn_backbone.x4", "cnn_backbone.x2", "feat_pyramid.0", "feat_pyramid.3", "transformer", "ctx0",
+              "global_refiner", "refiner.0.disp", "refiner.2.occ", "up4x.disp"):
+        err = (m.taps[k] - ot[k]).abs().max().item()
+        assert err < 5e-4 * max(1.0, ot[k].abs().max().item()), (k, err)
+    assert torch.equal(m.taps["disp_init.argmax"], ot["disp_init.argmax"])
+
+
+def test_state_dict_surface_matches_reference_contract():
+    m = S2M2(32, 1, 1, use_positivity=True, refine_iter=1, precision="fp32")
+    sd = random_state_dict(32, 1, 2)
+    bad = dict(sd)
+    bad["ctx_feat.0.weight"] = torch.zeros(3, 3)          # wrong shape: skipped with a message (s2m2.py:69-78)
+    m.my_load_state_dict(bad)
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    assert torch.equal(out["ctx_feat.2.weight"], sd["ctx_feat.2.weight"])
+    assert float(out["ctx_feat.0.weight"].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        m.ops = TorchOps()
+        m(torch.zeros(1, 3, 60, 64), torch.zeros(1, 3, 60, 64))
