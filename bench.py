@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — stereo pairs/s of the S2M2 forward on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--model L] [--height 1024] [--width 1216] [--batch B]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+  python bench.py --impl reference ...     (the reference algorithm's CPU path = the oracle port, host cores)
+
+A "step" is one forward over `batch` synthetic stereo pairs per GPU (random-init weights of the named
+architecture, synthetic images — there is no network for checkpoints/datasets).
+  value      pairs/s with the inputs already resident in HBM (CUDA-graph replay of the whole forward),
+             CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e        the same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of both
+             images and D2H read of disparity/occlusion/confidence inside the timed region, every step.
+  roofline   dominant kernel = the implicit-GEMM convolution; the heaviest conv shape of the model is timed
+             alone with CUDA events; achieved = 2*M*N*K / time against MEASURED_PEAKS.json (burst figure).
+  cpu_baseline  the oracle (port of the reference's fp32 algorithm) on the host cores, rank 0, N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_PAIR = {  # 2*MAC over conv/linear/bmm, refine_iter=3  [TFLOP]
+    ("S", 480, 640): 0.763, ("L", 1024, 1216): 14.451, ("XL", 2048, 2432): 133.535,
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tensor_burst": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "src": "measured"}
+    return {"tensor_burst": 1590.0, "tensor_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, cfg_workload):
+    """--impl reference: the reference's CPU algorithm (oracle port, fp32 eager torch ops) on the host cores."""
+    from oracle import s2m2_oracle as O
+    from s2m2_b200.weights import MODEL_TABLE, random_state_dict, synthetic_pair
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C, NTR = MODEL_TABLE[args.model]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = random_state_dict(C, NTR, 0)
+    H, W = args.height, args.width
+    budget = float(os.environ.get("S2M2_REF_BUDGET_S", "150"))
+    # bounded sample: centre crop (multiple of 32) whose cost fits the budget; pairs/s extrapolated by pixel count
+    left, right = synthetic_pair(1, H, W, 1)
+    t0 = time.time()
+    O.forward(sd, left[..., :H // 4 // 32 * 32 or 32, :W // 4 // 32 * 32 or 32].contiguous(),
+              right[..., :H // 4 // 32 * 32 or 32, :W // 4 // 32 * 32 or 32].contiguous(), NTR, True, 3)
+    t_probe = time.time() - t0
+    hh, ww = (H // 4 // 32 * 32 or 32), (W // 4 // 32 * 32 or 32)
+    est_full = t_probe * (H * W) / (hh * ww)
+    nsteps = args.steps + args.warmup
+    frac = 1.0
+    if est_full * nsteps > budget:
+        frac = max(budget / (est_full * nsteps), (hh * ww) / (H * W))
+    sh = max(32, int(H * frac ** 0.5) // 32 * 32)
+    sw = max(32, int(W * frac ** 0.5) // 32 * 32)
+    l, r = left[..., :sh, :sw].contiguous(), right[..., :sh, :sw].contiguous()
+    for _ in range(args.warmup):
+        O.forward(sd, l, r, NTR, True, 3)
+    t0 = time.time()
+    for _ in range(args.steps):
+        O.forward(sd, l, r, NTR, True, 3)
+    dt = (time.time() - t0) / args.steps
+    pairs_per_s = (sh * sw) / (H * W) / dt
+    sample = f"oracle port fp32, {args.steps} steps of one {sw}x{sh} crop of a {W}x{H} pair ({sh * sw / (H * W):.3f} pair/step)"
+    line = {"impl": "reference", "metric": "stereo pairs/sec", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_workload,
+            "cpu_baseline": {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pairs_per_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def heaviest_conv(model, B, H, W):
+    """The conv launch with the most FLOPs in the schedule: found by recording conv shapes of one forward."""
+    rec = []
+    ops = model.ops
+    orig = ops.conv2d
+
+    def spy(x, cw, act, out, res=None, x2=None, **kw):
+        M = out.shape[0] * out.shape[1] * out.shape[2] // (4 if cw.shuffle else 1)
+        rec.append((2.0 * M * cw.cout * cw.kh * cw.kw * cw.cin, x, cw, act, out, res, x2))
+        return orig(x, cw, act, out, res, x2, **kw)
+    ops.conv2d = spy
+    return rec, (lambda: setattr(ops, "conv2d", orig))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="s2m2_b200", choices=["s2m2_b200", "reference"])
+    ap.add_argument("--model", default="L", choices=["S", "M", "L", "XL"])
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=1216)
+    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    H, W, B = args.height, args.width, args.batch
+    cfg = {"workload": f"{args.model} (CH/NTR per model_utils.py:12-17) {W}x{H} refine_iter=3, {B} pair(s)/GPU/step",
+           "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded pairs, NCCL weight broadcast only)",
+           "precision": args.precision, "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"}
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    from s2m2_b200.model import S2M2
+    from s2m2_b200.weights import MODEL_TABLE, random_state_dict, synthetic_pair
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    C, NTR = MODEL_TABLE[args.model]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = S2M2(C, 1, NTR, use_positivity=True, refine_iter=3, precision=args.precision).eval()
+    if rank == 0:
+        model.my_load_state_dict(random_state_dict(C, NTR, 0))
+    model = model.to(dev)
+    if world > 1:   # the only collective on the path: one flat weight broadcast over NVLink
+        flat = torch.cat([p.data.reshape(-1) for p in model._p.values()])
+        dist.broadcast(flat, 0)
+        off = 0
+        for p in model._p.values():
+            n = p.numel()
+            p.data.copy_(flat[off:off + n].view_as(p))
+            off += n
+        del flat
+        model._packed = None
+
+    left_h, right_h = synthetic_pair(B, H, W, 1 + rank)
+    left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
+    left, right = left_h.to(dev), right_h.to(dev)
+
+    # ---- warm-up (also builds packed weights, PE tables, func attributes), then capture the forward in a CUDA graph
+    with torch.inference_mode():
+        out = model(left, right)
+        torch.cuda.synchronize()
+        n0 = model.ops.launch_count()
+        out = model(left, right)
+        torch.cuda.synchronize()
+        launches_per_fwd = model.ops.launch_count() - n0
+        graph = None
+        if not args.no_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=s):
+                    out = model(left, right)
+            torch.cuda.current_stream().wait_stream(s)
+
+        def step():
+            if graph is not None:
+                graph.replay()
+            else:
+                model(left, right)
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- e2e: public nn.Module call with host inputs / host outputs, every step
+        host_out = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(3)]
+
+        def e2e_step():
+            if graph is not None:
+                left.copy_(left_h, non_blocking=True)      # H2D into the graph's static input buffers
+                right.copy_(right_h, non_blocking=True)
+                graph.replay()
+                res = out
+            else:
+                res = model(left_h.to(dev, non_blocking=True), right_h.to(dev, non_blocking=True))
+            for h, t in zip(host_out, res):
+                h.copy_(t, non_blocking=True)
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e3.record()
+        torch.cuda.synchronize()
+        ms_e2e = e2.elapsed_time(e3)
+
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+        # ---- roofline of the dominant kernel (implicit-GEMM conv), heaviest shape timed alone (rank 0)
+        roof = None
+        if rank == 0:
+            rec, restore = heaviest_conv(model, B, H, W)
+            model(left, right)
+            restore()
+            torch.cuda.synchronize()
+            flops, x, cw, act, o, res, x2 = max(rec, key=lambda r: r[0])
+            total_conv_flops = sum(r[0] for r in rec)
+            for _ in range(3):
+                model.ops.conv2d(x, cw, act, o, None, x2)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            torch.cuda.synchronize()
+            k0.record()
+            for _ in range(reps):
+                model.ops.conv2d(x, cw, act, o, None, x2)
+            k1.record()
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1) / reps
+            pk = _peaks()
+            ach = flops / (kms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": ach / pk["tensor_burst"],
+                    "traffic": None, "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
+                    "kernel": f"implicit-GEMM conv {cw.name}: M={o.shape[0] * o.shape[1] * o.shape[2]} N={cw.cout} K={cw.kh * cw.kw * cw.cin}",
+                    "kernel_ms": kms, "kernel_gflop": flops / 1e9, "conv_gflop_per_step": total_conv_flops / 1e9}
+
+    pairs = B * world * args.steps
+    value = pairs / (ms * 1e-3)
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    tf = FLOP_PER_PAIR.get((args.model, H, W))
+    pk = _peaks()
+    line = {"metric": "stereo pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / 11.2) if (args.model, H, W) == ("L", 1024, 1216) else None,
+            "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4,
+                    "d2h_bytes_per_step": 3 * B * H * W * 4},
+            "gpu_launches": launches_per_fwd * args.steps, "launches_per_forward": launches_per_fwd,
+            "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof}
+    if tf:
+        ach = value / world * tf
+        line["roofline_forward"] = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                                    "frac": ach / pk["tensor_sustained"], "tflop_per_pair": tf,
+                                    "peak_source": pk["src"] + " bf16 sustained"}
+    line["vs_baseline_note"] = "value / 11.2 FPS (reference README TensorRT fp16 on ONE RTX 5090, L@1216x1024; BASELINE.md section 1)"
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import s2m2_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = random_state_dict(C, NTR, 0)
+        sh, sw = (H, W) if H * W <= 640 * 480 else (H // 2 // 32 * 32, W // 2 // 32 * 32)
+        l, r = left_h[:1, :, :sh, :sw].contiguous(), right_h[:1, :, :sh, :sw].contiguous()
+        O.forward(sd, l[..., :64, :64].contiguous(), r[..., :64, :64].contiguous(), NTR, True, 3)   # thread-pool warm-up
+        t0 = time.time()
+        O.forward(sd, l, r, NTR, True, 3)
+        dt = time.time() - t0
+        line["cpu_baseline"] = {"value": (sh * sw) / (H * W) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle port fp32 eager, one {sw}x{sh} crop of a {W}x{H} pair ({dt:.1f} s), scaled by pixel count"}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+/*
+ * s2m2b200 — C-ABI of the Blackwell-native (sm_100a) S2M2 stereo inference kernels.
+ *
+ * The reference (junhong-3dv/s2m2) is pure Python/PyTorch and has no FFI of its own: its boundary
+ * is the nn.Module surface S2M2.forward (src/s2m2/core/model/s2m2.py:136-197).  This header is the
+ * operator-level boundary that the replacement module (s2m2_b200/model.py) binds through ctypes;
+ * each entry point names the reference code it replaces.  Plain pointers and sizes only — no torch
+ * types.  All pointers are DEVICE pointers unless stated otherwise; `stream` is a cudaStream_t.
+ *
+ * Conventions
+ *   - Activations are NHWC.  An S2m2Tensor describes a view: pixel p=(n*H+y)*W+x starts at
+ *     ptr + p*ld elements, channels are contiguous.  `ld >= C` lets a view be a channel slice of a
+ *     wider buffer (this is how torch.cat is avoided).
+ *   - dtype: 0 = float32, 1 = float16.  GEMM-class kernels accumulate in fp32.
+ *   - Every function returns 0 on success and a negative code on error; s2m2b200_last_error()
+ *     returns a thread-local message.  Kernels are enqueued on `stream`, nothing synchronises.
+ *   - Ownership: the caller owns every buffer.  The library keeps no state between calls except
+ *     cached cudaFuncAttributes / TMA descriptors (not thread-safe; one host thread per device).
+ */
+#ifndef S2M2B200_H_
+#define S2M2B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2M2_F32 0
+#define S2M2_F16 1
+
+#define S2M2_ACT_NONE 0
+#define S2M2_ACT_GELU 1     /* exact erf GELU (nn.GELU default) */
+#define S2M2_ACT_RELU 2
+#define S2M2_ACT_SIGMOID 3
+#define S2M2_ACT_TANH 4
+
+typedef struct {
+  void* ptr;
+  int32_t dtype;
+  int32_t N, H, W, C;
+  int64_t ld;
+} S2m2Tensor;
+
+/* Implicit-GEMM convolution / linear layer:
+ *   y[p, co] = act( sum_{ky,kx,ci} xcat[p*stride - pad + (ky,kx), ci] * w[co, (ky*KW+kx)*Cin + ci] + bias[co] ) (+ res[p, co])
+ * where xcat = concat(x, x2) along channels (x2 optional: x2.ptr == NULL), zero padding.
+ * Replaces every nn.Conv2d / nn.Linear / nn.ConvTranspose2d on the path (attentions.py:24-30,71-74,
+ * 239-241,269-275; submodules.py:70-86,104-108,127-135; feature_fusion.py:14-21; refinenet.py:14-20,
+ * 47-57,87-122; unet.py:25-37; stacked_MRT.py:22-34; s2m2.py:65-67), with the activation, the residual
+ * add and the concat of the callers fused in.
+ *   shuffle2x2 != 0: ConvTranspose2d(k=2,s=2) — GEMM columns are (a*2+b)*Cr + co (Cr = Cout/4) and are
+ *   scattered to y[n, 2*oy+a, 2*ox+b, co]; y must be (N, 2*Ho, 2*Wo, Cr).
+ *   batch > 1: independent GEMMs; x/w/y pointers advance by x_bs/w_bs/y_bs elements per batch entry
+ *   (used for the per-scan-line correlation that builds the cost volume, submodules.py:216-217).
+ * w dtype = w_dtype (same as x unless x is fp32 scalar maps feeding fp16 weights); bias is fp32. */
+typedef struct {
+  S2m2Tensor x, x2, y, res;     /* x2.ptr / res.ptr may be NULL */
+  const void* w;
+  int32_t w_dtype;
+  const float* bias;            /* may be NULL */
+  int32_t KH, KW, stride, pad_h, pad_w;
+  int32_t Cout;                 /* GEMM N (4*Cr when shuffle2x2) */
+  int32_t act;
+  int32_t shuffle2x2;
+  int32_t batch;                /* >= 1 */
+  int64_t x_bs, w_bs, y_bs;
+  int32_t impl;                 /* 0 = auto, 1 = force CUDA-core fp32 FMA kernel, 2 = force tcgen05 kernel */
+} S2m2Conv;
+int s2m2b200_conv2d(const S2m2Conv* a, void* stream);
+
+/* Multi-head attention over S sequences of N tokens (F.scaled_dot_product_attention /
+ * explicit softmax, attentions.py:33-54,77-96).  qkv is the fused projection output: token t of
+ * sequence s is row s*N+t; q,k,v at channel offsets 0, C, 2C; head h uses channels [h*d,(h+1)*d).
+ * Keys/values are taken from sequence (s + kv_shift) % S (symmetric cross attention: kv_shift = S/2).
+ * If pesum.ptr != NULL the contextual relative positional term of attentions.py:46-47 is produced:
+ *   pesum[s,t,h,0:16]  = sum_j P[t,j] * 0.5*pe_x[x_t - x_j + pw - 1]
+ *   pesum[s,t,h,16:32] = sum_j P[t,j] * 0.5*pe_y[y_t - y_j + ph - 1],  token t = y*pw + x
+ * (the (N,N,32) tensor of utils.py:32-60 is never materialised). */
+int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, int32_t N, int32_t heads,
+                       int32_t kv_shift, const float* pe_x, const float* pe_y, int32_t ph, int32_t pw,
+                       const S2m2Tensor* pesum, void* stream);
+
+/* Relative-PE table of utils.py:32-60 for one axis of length n: HOST output (2n+1, 16) floats. */
+int s2m2b200_pe_table(int32_t n, float* host_out);
+
+/* LayerNorm over C, eps 1e-5; gamma/beta NULL = no affine (attentions.py:117,...; submodules.py:165). */
+int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* gamma, const float* beta, void* stream);
+/* GroupNorm(groups, C), eps 1e-5, affine (submodules.py:80,90).  work: 2*N*groups doubles. */
+int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups, const float* gamma,
+                       const float* beta, double* work, void* stream);
+/* AvgPool2d(2) (unet.py:25) and Upsample(x2, bilinear, align_corners=False) (unet.py:32). */
+int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream);
+int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream);
+/* out = f + w*z0 + (1-w)*z1, w = clamp(g, .01, .99) with g already sigmoid-ed (feature_fusion.py:27-29). */
+int s2m2b200_gate_blend(const S2m2Tensor* f, const S2m2Tensor* g, const S2m2Tensor* z0, const S2m2Tensor* z1,
+                        const S2m2Tensor* out, void* stream);
+int s2m2b200_copy_channels(const S2m2Tensor* src, const S2m2Tensor* dst, void* stream);
+int s2m2b200_unary(const S2m2Tensor* x, const S2m2Tensor* y, int32_t act, void* stream);
+int s2m2b200_mul(const S2m2Tensor* a, const S2m2Tensor* b, const S2m2Tensor* out, void* stream);
+/* h = (1-z)*h + z*q in place (refinenet.py:29,35). */
+int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tensor* h, void* stream);
+/* (x/255-.5)*2 of both NCHW fp32 images, stacked [left..., right...] on N, to NHWC (s2m2.py:86-96). */
+int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W,
+                        const S2m2Tensor* out, void* stream);
+
+/* Dust-bin log-Sinkhorn + argmax + 5-tap soft-argmax over the (B,h,w,w) fp32 cost volume
+ * (submodules.py:147-243): disp/conf/occ (B,h,w) fp32, amax int32 = prob_max_ind (submodules.py:226). */
+int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t w, float* disp, float* conf,
+                                 float* occ, int32_t* amax, int32_t use_positivity, int32_t iters, void* stream);
+/* CostVolume.__call__ (submodules.py:39-60): out (B,h,w,18) fp32 = 9 taps level 1 | 9 taps pooled level, /16. */
+int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h, int32_t w, float* out, void* stream);
+
+/* GlobalRefiner glue (refinenet.py:63-66,72): out[...,0] = disp/100*mask, out[...,1] = logit(mask*conf, .1). */
+int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t npix, const S2m2Tensor* out, void* stream);
+/* disp = mask*disp + (1-mask)*upd (upd pre-scaled by 100), optional clamp >= 0 (s2m2.py:160-161). */
+int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t npix,
+                                  int32_t use_positivity, void* stream);
+/* LocalRefiner glue (refinenet.py:134-135,140): small (npix,4) = disp/100 | logit(conf,.01) | logit(occ,.01) | 0. */
+int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const float* occ, int64_t npix,
+                                float* small, void* stream);
+/* refinenet.py:147-154 + s2m2.py:177-180: disp += dd; conf/occ = sigmoid(delta + logit); clamp; occ *= (x - disp >= 0). */
+int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* dd,
+                                  const float* co, int32_t B, int32_t h, int32_t w, int32_t use_positivity, void* stream);
+
+/* RAFT convex 4x upsampling of disp*4 | occ | conf with one set of 9 logits (s2m2.py:101-114,184-187):
+ * logits (B,4h,4w,9) fp32 -> up (B,4h,4w,4) fp32 (4th channel 0). */
+int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits,
+                               int32_t B, int32_t h, int32_t w, float* up, void* stream);
+/* 9-tap softmax filter at full resolution (s2m2.py:116-133,190-193): out (3,B,1,H,W) planar fp32. */
+int s2m2b200_filter1x(const float* up, const float* logits, int32_t B, int32_t H, int32_t W, float* out, void* stream);
+
+const char* s2m2b200_last_error(void);
+/* Version / capability string, e.g. "s2m2b200 0.1 sm_100a tcgen05". */
+const char* s2m2b200_version(void);
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t s2m2b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2M2B200_H_ */

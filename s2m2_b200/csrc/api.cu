@@ -1,0 +1,87 @@
+// C-ABI glue: error state, conv dispatch (CUDA-core vs tcgen05), host-side PE table.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace s2m2 {
+
+static thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int conv_simt_launch(const S2m2Conv* a, cudaStream_t s);
+int conv_tc_supported(const S2m2Conv* a);
+int conv_tc_launch(const S2m2Conv* a, cudaStream_t s);
+
+}  // namespace s2m2
+
+using namespace s2m2;
+
+extern "C" {
+
+const char* s2m2b200_last_error(void) { return g_err; }
+const char* s2m2b200_version(void) { return "s2m2b200 0.1 sm_100a (cuda-core fp32 + tcgen05 f16 implicit GEMM)"; }
+int64_t s2m2b200_launch_count(void) { return g_launches; }
+
+int s2m2b200_conv2d(const S2m2Conv* a, void* stream) {
+  const S2m2Tensor &x = a->x, &y = a->y;
+  S2M2_CHECK(x.ptr && y.ptr && a->w, "conv2d: null pointer");
+  S2M2_CHECK(a->KH > 0 && a->KW > 0 && a->stride > 0 && a->Cout > 0, "conv2d: bad geometry");
+  const int Ho = (x.H + 2 * a->pad_h - a->KH) / a->stride + 1, Wo = (x.W + 2 * a->pad_w - a->KW) / a->stride + 1;
+  if (a->x2.ptr) {
+    S2M2_CHECK(a->x2.N == x.N && a->x2.H == x.H && a->x2.W == x.W && a->x2.dtype == x.dtype, "conv2d: x2 must match x");
+  }
+  if (a->shuffle2x2) {
+    S2M2_CHECK(a->Cout % 4 == 0 && y.C == a->Cout / 4 && y.H == 2 * Ho && y.W == 2 * Wo && y.N == x.N && !a->res.ptr,
+               "conv2d(shuffle): y must be (N,2Ho,2Wo,Cout/4) and no residual");
+  } else {
+    S2M2_CHECK(y.C == a->Cout && y.H == Ho && y.W == Wo && y.N == x.N, "conv2d: y shape (%d,%d,%d,%d) != expected (%d,%d,%d,%d)",
+               y.N, y.H, y.W, y.C, x.N, Ho, Wo, a->Cout);
+    if (a->res.ptr) S2M2_CHECK(a->res.C == y.C && npix(a->res) == npix(y), "conv2d: residual shape mismatch");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->impl == 2) {
+    S2M2_CHECK(conv_tc_supported(a), "conv2d: tcgen05 kernel forced but shape/dtype unsupported");
+    return conv_tc_launch(a, s);
+  }
+  if (a->impl == 0 && conv_tc_supported(a)) return conv_tc_launch(a, s);
+  return conv_simt_launch(a, s);
+}
+
+// utils.py:32-60 — one axis of the relative positional table.  torch.linspace semantics: the first half
+// is start + i*step, the second half end - (n-1-i)*step.
+static float linspace_at(float start, float end, int n, int i) {
+  if (n == 1) return start;
+  float step = (end - start) / (float)(n - 1);
+  return i < n / 2 ? start + (float)i * step : end - (float)(n - 1 - i) * step;
+}
+
+int s2m2b200_pe_table(int32_t n, float* host_out) {
+  S2M2_CHECK(n > 0 && host_out, "pe_table: bad arguments");
+  const int L = 2 * n + 1, D = 16;
+  const float sig = 5.0f / 32.0f;
+  for (int r = 0; r < L; ++r) {
+    float pos = tanhf(linspace_at(-3.f, 3.f, L, r));
+    float row[16];
+    float nrm = 0.f;
+    for (int c = 0; c < D; ++c) {
+      float x = (linspace_at(-1.f, 1.f, D, c) - pos) / sig;
+      float v = fabsf(x) < 1e-6f ? 1.0f : sinf(3.1415f * x) / (3.1415f * x);  // literal 3.1415 as in utils.py:6
+      row[c] = v;
+      nrm += v * v;
+    }
+    nrm = fmaxf(sqrtf(nrm), 1e-12f);  // F.normalize eps
+    for (int c = 0; c < D; ++c) host_out[r * D + c] = row[c] / nrm;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Shared device/host helpers for the s2m2b200 kernels (sm_100a).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/s2m2b200.h"
+
+namespace s2m2 {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern long long g_launches;
+
+#define S2M2_CHECK(cond, ...)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      s2m2::set_error(__VA_ARGS__);           \
+      return -1;                              \
+    }                                         \
+  } while (0)
+
+#define S2M2_LAUNCH_OK(name)                                                        \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      s2m2::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
+      return -2;                                                                    \
+    }                                                                               \
+    ++s2m2::g_launches;                                                             \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- dtype-agnostic element access ---------------------------------------------------------------
+__device__ __forceinline__ float ld1(const void* p, long long i, int half) {
+  return half ? __half2float(((const __half*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st1(void* p, long long i, int half, float v) {
+  if (half) ((__half*)p)[i] = __float2half_rn(v);
+  else ((float*)p)[i] = v;
+}
+// 4 consecutive elements; i must be a multiple of 4 and the base suitably aligned (16 B fp32 / 8 B fp16)
+__device__ __forceinline__ float4 ld4(const void* p, long long i, int half) {
+  if (half) {
+    uint2 r = *(const uint2*)((const __half*)p + i);
+    __half2 a = *(__half2*)&r.x, b = *(__half2*)&r.y;
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  return *(const float4*)((const float*)p + i);
+}
+__device__ __forceinline__ void st4(void* p, long long i, int half, float4 v) {
+  if (half) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *(uint32_t*)&a;
+    r.y = *(uint32_t*)&b;
+    *(uint2*)((__half*)p + i) = r;
+  } else {
+    *(float4*)((float*)p + i) = v;
+  }
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case S2M2_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case S2M2_ACT_RELU: return fmaxf(x, 0.0f);
+    case S2M2_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case S2M2_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+static inline size_t esize(int dtype) { return dtype == S2M2_F16 ? 2 : 4; }
+// can a tensor view be accessed with 4-element vectors?
+static inline bool vec4_ok(const S2m2Tensor& t) {
+  return t.C % 4 == 0 && t.ld % 4 == 0 && aligned(t.ptr, 4 * esize(t.dtype));
+}
+static inline long long npix(const S2m2Tensor& t) { return (long long)t.N * t.H * t.W; }
+
+}  // namespace s2m2

@@ -1,0 +1,401 @@
+// Bandwidth-bound kernels: norms, resampling, gates, layout conversion, refiner glue.  All NHWC, any pixel
+// stride, fp32 or fp16 storage (runtime flag), fp32 math.  Reference lines: see include/s2m2b200.h.
+#include "common.cuh"
+
+namespace s2m2 {
+
+struct TV {  // device-side tensor view
+  void* p;
+  long long ld;
+  int half;
+  int C;
+};
+static inline TV tv(const S2m2Tensor& t) { return TV{t.ptr, t.ld, t.dtype == S2M2_F16, t.C}; }
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 32;  // a few waves of the 148 SMs; kernels are grid-stride
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C (one warp per pixel, two-pass in registers)
+// ------------------------------------------------------------------------------------------------
+template <int MAXI>
+__global__ void layernorm_kernel(TV x, TV y, const float* __restrict__ gamma, const float* __restrict__ beta, long long npix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int C = x.C;
+  for (long long pix = warp; pix < npix; pix += nwarps) {
+    float v[MAXI];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      int c = lane + 32 * i;
+      v[i] = c < C ? ld1(x.p, pix * x.ld + c, x.half) : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      int c = lane + 32 * i;
+      float d = c < C ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      int c = lane + 32 * i;
+      if (c < C) {
+        float o = (v[i] - mean) * rstd;
+        if (gamma) o = o * gamma[c] + beta[c];
+        st1(y.p, pix * y.ld + c, y.half, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm: stats (sum, sumsq per (image, group) in double) then apply
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, double* __restrict__ stats) {
+  extern __shared__ float sh[];  // [groups][2]
+  const int n = blockIdx.y, C = x.C, cpg = C / groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = lane; c < C; c += 32) {
+    float s = 0.f, q = 0.f;
+    for (int pp = p0 + wid; pp < p1; pp += nw) {
+      float v = ld1(x.p, ((long long)n * HW + pp) * x.ld + c, x.half);
+      s += v;
+      q += v * v;
+    }
+    atomicAdd(&sh[(c / cpg) * 2 + 0], s);
+    atomicAdd(&sh[(c / cpg) * 2 + 1], q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sh[i]);
+}
+
+__global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, long long total4) {
+  const int C = x.C, C4 = C / 4, cpg = C / groups;
+  const double cnt = (double)HW * cpg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / C4;
+    int c = (int)(i - pix * C4) * 4;
+    int n = (int)(pix / HW);
+    float4 v = ld4(x.p, pix * x.ld + c, x.half);
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int g = (c + k) / cpg;
+      double s = stats[((long long)n * groups + g) * 2], q = stats[((long long)n * groups + g) * 2 + 1];
+      double mean = s / cnt;
+      double var = q / cnt - mean * mean;
+      float rstd = rsqrtf((float)(var > 0 ? var : 0) + 1e-5f);
+      o[k] = (o[k] - (float)mean) * rstd * gamma[c + k] + beta[c + k];
+    }
+    st4(y.p, pix * y.ld + c, y.half, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resampling
+// ------------------------------------------------------------------------------------------------
+__global__ void avgpool2_kernel(TV x, TV y, int N, int H, int W, long long total4) {
+  const int C4 = x.C / 4, Ho = H / 2, Wo = W / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / C4;
+    int c = (int)(i - pix * C4) * 4;
+    int ox = (int)(pix % Wo);
+    long long t = pix / Wo;
+    int oy = (int)(t % Ho);
+    long long n = t / Ho;
+    long long b = (n * H + 2 * oy) * W + 2 * ox;
+    float4 a0 = ld4(x.p, b * x.ld + c, x.half), a1 = ld4(x.p, (b + 1) * x.ld + c, x.half);
+    float4 a2 = ld4(x.p, (b + W) * x.ld + c, x.half), a3 = ld4(x.p, (b + W + 1) * x.ld + c, x.half);
+    float4 o = make_float4((a0.x + a1.x + a2.x + a3.x) * 0.25f, (a0.y + a1.y + a2.y + a3.y) * 0.25f,
+                           (a0.z + a1.z + a2.z + a3.z) * 0.25f, (a0.w + a1.w + a2.w + a3.w) * 0.25f);
+    st4(y.p, pix * y.ld + c, y.half, o);
+  }
+}
+
+// bilinear x2, align_corners=False: src = (dst + .5)/2 - .5 clamped at 0 (torch semantics)
+__global__ void upsample2x_kernel(TV x, TV y, int N, int H, int W, long long total4) {
+  const int C4 = x.C / 4, Ho = 2 * H, Wo = 2 * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / C4;
+    int c = (int)(i - pix * C4) * 4;
+    int ox = (int)(pix % Wo);
+    long long t = pix / Wo;
+    int oy = (int)(t % Ho);
+    long long n = t / Ho;
+    float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+    int y0 = (int)sy, x0 = (int)sx;
+    int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    long long r0 = (n * H + y0) * W, r1 = (n * H + y1) * W;
+    float4 a = ld4(x.p, (r0 + x0) * x.ld + c, x.half), b = ld4(x.p, (r0 + x1) * x.ld + c, x.half);
+    float4 d = ld4(x.p, (r1 + x0) * x.ld + c, x.half), e = ld4(x.p, (r1 + x1) * x.ld + c, x.half);
+    float4 o;
+    o.x = hy * (hx * a.x + lx * b.x) + ly * (hx * d.x + lx * e.x);
+    o.y = hy * (hx * a.y + lx * b.y) + ly * (hx * d.y + lx * e.y);
+    o.z = hy * (hx * a.z + lx * b.z) + ly * (hx * d.z + lx * e.z);
+    o.w = hy * (hx * a.w + lx * b.w) + ly * (hx * d.w + lx * e.w);
+    st4(y.p, pix * y.ld + c, y.half, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise (vector of 4 channels per thread)
+// ------------------------------------------------------------------------------------------------
+enum { EW_COPY = 0, EW_UNARY = 1, EW_MUL = 2, EW_GRU = 3, EW_BLEND = 4 };
+
+template <int OP>
+__global__ void ew_kernel(TV a, TV b, TV c, TV d, TV o, int act, long long total4) {
+  const int C4 = o.C / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / C4;
+    int ch = (int)(i - pix * C4) * 4;
+    float4 r;
+    if (OP == EW_COPY) {
+      r = ld4(a.p, pix * a.ld + ch, a.half);
+    } else if (OP == EW_UNARY) {
+      float4 v = ld4(a.p, pix * a.ld + ch, a.half);
+      r = make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act));
+    } else if (OP == EW_MUL) {
+      float4 v = ld4(a.p, pix * a.ld + ch, a.half), w = ld4(b.p, pix * b.ld + ch, b.half);
+      r = make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w);
+    } else if (OP == EW_GRU) {  // a=z, b=q, o=h (in place): h = (1-z)h + z q
+      float4 z = ld4(a.p, pix * a.ld + ch, a.half), q = ld4(b.p, pix * b.ld + ch, b.half);
+      float4 h = ld4(o.p, pix * o.ld + ch, o.half);
+      r = make_float4((1.f - z.x) * h.x + z.x * q.x, (1.f - z.y) * h.y + z.y * q.y, (1.f - z.z) * h.z + z.z * q.z,
+                      (1.f - z.w) * h.w + z.w * q.w);
+    } else {  // EW_BLEND: a=f, b=g, c=z0, d=z1
+      float4 f = ld4(a.p, pix * a.ld + ch, a.half), g = ld4(b.p, pix * b.ld + ch, b.half);
+      float4 z0 = ld4(c.p, pix * c.ld + ch, c.half), z1 = ld4(d.p, pix * d.ld + ch, d.half);
+      float w0 = fminf(fmaxf(g.x, 0.01f), 0.99f), w1 = fminf(fmaxf(g.y, 0.01f), 0.99f);
+      float w2 = fminf(fmaxf(g.z, 0.01f), 0.99f), w3 = fminf(fmaxf(g.w, 0.01f), 0.99f);
+      r = make_float4(f.x + w0 * z0.x + (1.f - w0) * z1.x, f.y + w1 * z0.y + (1.f - w1) * z1.y,
+                      f.z + w2 * z0.z + (1.f - w2) * z1.z, f.w + w3 * z0.w + (1.f - w3) * z1.w);
+    }
+    st4(o.p, pix * o.ld + ch, o.half, r);
+  }
+}
+
+__global__ void preprocess_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W, TV o) {
+  const long long HW = (long long)H * W, total = 2LL * B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / HW, hw = i - n * HW;
+    const float* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st1(o.p, i * o.ld + c, o.half, (src[c * HW + hw] / 255.f - 0.5f) * 2.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// refiner glue on the 1/4-resolution scalar maps (fp32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float logit_eps(float x, float eps) {
+  x = fminf(fmaxf(x, eps), 1.f - eps);
+  return logf(x / (1.f - x));
+}
+
+__global__ void gr_prep_kernel(const float* __restrict__ disp, const float* __restrict__ conf, long long n, TV o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float c = conf[i], m = c > 0.2f ? 1.f : 0.f;
+    st1(o.p, i * o.ld + 0, o.half, disp[i] / 100.f * m);
+    st1(o.p, i * o.ld + 1, o.half, logit_eps(m * c, 0.1f));
+  }
+}
+
+__global__ void gr_merge_kernel(float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ upd,
+                                long long n, int pos) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float m = conf[i] > 0.2f ? 1.f : 0.f;
+    float d = m * disp[i] + (1.f - m) * upd[i];
+    disp[i] = pos ? fmaxf(d, 0.f) : d;
+  }
+}
+
+__global__ void lr_prep_kernel(const float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ occ,
+                               long long n, float4* __restrict__ small) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    small[i] = make_float4(disp[i] / 100.f, logit_eps(conf[i], 0.01f), logit_eps(occ[i], 0.01f), 0.f);
+}
+
+__global__ void lr_update_kernel(float* __restrict__ disp, float* __restrict__ conf, float* __restrict__ occ,
+                                 const float4* __restrict__ small, const float* __restrict__ dd, const float* __restrict__ co,
+                                 long long n, int w, int pos) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = small[i];
+    float d = disp[i] + dd[i];
+    if (pos) d = fmaxf(d, 0.f);
+    float x = (float)(i % w);
+    conf[i] = 1.f / (1.f + expf(-(co[2 * i] + s.y)));
+    float o = 1.f / (1.f + expf(-(co[2 * i + 1] + s.z)));
+    occ[i] = (x - d >= 0.f) ? o : 0.f;
+    disp[i] = d;
+  }
+}
+
+}  // namespace s2m2
+
+using namespace s2m2;
+
+// ==================================================================================================
+// C-ABI
+// ==================================================================================================
+extern "C" {
+
+int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* gamma, const float* beta, void* stream) {
+  S2M2_CHECK(x->C == y->C && npix(*x) == npix(*y), "layernorm: shape mismatch");
+  S2M2_CHECK(x->C <= 1024, "layernorm: C=%d > 1024", x->C);
+  S2M2_CHECK((gamma == nullptr) == (beta == nullptr), "layernorm: gamma/beta must both be given or both NULL");
+  long long n = npix(*x);
+  int block = 256, grid = grid_for(n * 32, block);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x->C <= 128) layernorm_kernel<4><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
+  else if (x->C <= 256) layernorm_kernel<8><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
+  else if (x->C <= 512) layernorm_kernel<16><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
+  else layernorm_kernel<32><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
+  S2M2_LAUNCH_OK("layernorm");
+  return 0;
+}
+
+int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups, const float* gamma, const float* beta,
+                       double* work, void* stream) {
+  S2M2_CHECK(x->C == y->C && npix(*x) == npix(*y), "groupnorm: shape mismatch");
+  S2M2_CHECK(groups > 0 && x->C % groups == 0 && groups <= 64, "groupnorm: bad groups");
+  S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "groupnorm: needs C,ld multiples of 4 and aligned bases");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = x->H * x->W;
+  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2 * x->N * groups, s);
+  S2M2_CHECK(e == cudaSuccess, "groupnorm: memset failed: %s", cudaGetErrorString(e));
+  const int ppb = 256;
+  dim3 grid(cdiv(HW, ppb), x->N);
+  gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(float), s>>>(tv(*x), HW, groups, ppb, work);
+  S2M2_LAUNCH_OK("gn_stats");
+  long long total4 = npix(*x) * (x->C / 4);
+  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, work, gamma, beta, total4);
+  S2M2_LAUNCH_OK("gn_apply");
+  return 0;
+}
+
+int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
+  S2M2_CHECK(x->C == y->C && y->H == x->H / 2 && y->W == x->W / 2 && x->N == y->N && x->H % 2 == 0 && x->W % 2 == 0,
+             "avgpool2: shape mismatch");
+  S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "avgpool2: needs C,ld multiples of 4 and aligned bases");
+  long long total4 = npix(*y) * (y->C / 4);
+  avgpool2_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*y), x->N, x->H, x->W, total4);
+  S2M2_LAUNCH_OK("avgpool2");
+  return 0;
+}
+
+int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
+  S2M2_CHECK(x->C == y->C && y->H == x->H * 2 && y->W == x->W * 2 && x->N == y->N, "upsample2x: shape mismatch");
+  S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "upsample2x: needs C,ld multiples of 4 and aligned bases");
+  long long total4 = npix(*y) * (y->C / 4);
+  upsample2x_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*y), x->N, x->H, x->W, total4);
+  S2M2_LAUNCH_OK("upsample2x");
+  return 0;
+}
+
+static int ew_check(const S2m2Tensor* o, const S2m2Tensor* const* ins, int n, const char* name) {
+  S2M2_CHECK(vec4_ok(*o), "%s: output needs C,ld multiples of 4 and an aligned base", name);
+  for (int i = 0; i < n; ++i) {
+    S2M2_CHECK(ins[i]->C == o->C && npix(*ins[i]) == npix(*o), "%s: shape mismatch (input %d)", name, i);
+    S2M2_CHECK(vec4_ok(*ins[i]), "%s: input %d needs C,ld multiples of 4 and an aligned base", name, i);
+  }
+  return 0;
+}
+
+int s2m2b200_gate_blend(const S2m2Tensor* f, const S2m2Tensor* g, const S2m2Tensor* z0, const S2m2Tensor* z1,
+                        const S2m2Tensor* out, void* stream) {
+  const S2m2Tensor* ins[4] = {f, g, z0, z1};
+  if (int r = ew_check(out, ins, 4, "gate_blend")) return r;
+  long long total4 = npix(*out) * (out->C / 4);
+  ew_kernel<EW_BLEND><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*f), tv(*g), tv(*z0), tv(*z1), tv(*out), 0, total4);
+  S2M2_LAUNCH_OK("gate_blend");
+  return 0;
+}
+
+int s2m2b200_copy_channels(const S2m2Tensor* src, const S2m2Tensor* dst, void* stream) {
+  const S2m2Tensor* ins[1] = {src};
+  if (int r = ew_check(dst, ins, 1, "copy_channels")) return r;
+  long long total4 = npix(*dst) * (dst->C / 4);
+  ew_kernel<EW_COPY><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*src), tv(*src), tv(*src), tv(*src), tv(*dst), 0, total4);
+  S2M2_LAUNCH_OK("copy_channels");
+  return 0;
+}
+
+int s2m2b200_unary(const S2m2Tensor* x, const S2m2Tensor* y, int32_t act, void* stream) {
+  const S2m2Tensor* ins[1] = {x};
+  if (int r = ew_check(y, ins, 1, "unary")) return r;
+  long long total4 = npix(*y) * (y->C / 4);
+  ew_kernel<EW_UNARY><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*x), tv(*x), tv(*x), tv(*y), act, total4);
+  S2M2_LAUNCH_OK("unary");
+  return 0;
+}
+
+int s2m2b200_mul(const S2m2Tensor* a, const S2m2Tensor* b, const S2m2Tensor* out, void* stream) {
+  const S2m2Tensor* ins[2] = {a, b};
+  if (int r = ew_check(out, ins, 2, "mul")) return r;
+  long long total4 = npix(*out) * (out->C / 4);
+  ew_kernel<EW_MUL><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*a), tv(*b), tv(*a), tv(*a), tv(*out), 0, total4);
+  S2M2_LAUNCH_OK("mul");
+  return 0;
+}
+
+int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tensor* h, void* stream) {
+  const S2m2Tensor* ins[2] = {z, q};
+  if (int r = ew_check(h, ins, 2, "gru_update")) return r;
+  long long total4 = npix(*h) * (h->C / 4);
+  ew_kernel<EW_GRU><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*z), tv(*q), tv(*z), tv(*z), tv(*h), 0, total4);
+  S2M2_LAUNCH_OK("gru_update");
+  return 0;
+}
+
+int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
+                        void* stream) {
+  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 3, "preprocess: output must be (2B,H,W,3)");
+  preprocess_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, tv(*out));
+  S2M2_LAUNCH_OK("preprocess");
+  return 0;
+}
+
+int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n, const S2m2Tensor* out, void* stream) {
+  S2M2_CHECK(out->C == 2 && npix(*out) == n, "global_refiner_prep: output must be a 2-channel view of npix pixels");
+  gr_prep_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, n, tv(*out));
+  S2M2_LAUNCH_OK("global_refiner_prep");
+  return 0;
+}
+
+int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t n, int32_t pos, void* stream) {
+  gr_merge_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, upd, n, pos);
+  S2M2_LAUNCH_OK("global_refiner_merge");
+  return 0;
+}
+
+int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const float* occ, int64_t n, float* small, void* stream) {
+  S2M2_CHECK(aligned(small, 16), "local_refiner_prep: small must be 16-byte aligned");
+  lr_prep_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, n, (float4*)small);
+  S2M2_LAUNCH_OK("local_refiner_prep");
+  return 0;
+}
+
+int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* dd, const float* co,
+                                  int32_t B, int32_t h, int32_t w, int32_t pos, void* stream) {
+  long long n = (long long)B * h * w;
+  lr_update_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, (const float4*)small, dd, co, n, w, pos);
+  S2M2_LAUNCH_OK("local_refiner_update");
+  return 0;
+}
+
+}  // extern "C"

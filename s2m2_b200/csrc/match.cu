@@ -1,0 +1,290 @@
+// Matching-stage kernels on the fp32 scan-line cost volume: dust-bin log-Sinkhorn + argmax + soft-argmax,
+// cost-volume lookup, convex upsampling.  HBM/L2-bound work; warp-shuffle reductions, no tensor cores.
+// Reference: submodules.py:7-60,147-243; s2m2.py:101-133; utils.py:9-20.
+#include "common.cuh"
+
+namespace s2m2 {
+
+// ------------------------------------------------------------------------------------------------
+// Sinkhorn + argmax + 5-tap soft-argmax.  One CTA per scan-line (b, y): the (w x w) row matrix is
+// streamed from L2 once per half-iteration (2*iters + 1 passes); u, v live in shared memory.
+//   A(i,j) = cv[i,j] (or -1e4 where j > i when use_positivity), dust-bin row/column = 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_THREADS = 256;
+constexpr int SK_WARPS = SK_THREADS / 32;
+
+__device__ __forceinline__ float sk_a(const float* __restrict__ row_i, int i, int j, int w, int pos) {
+  // caller guarantees i < w
+  if (j >= w) return 0.f;
+  if (pos && j > i) return -1e4f;
+  return row_i[j];
+}
+
+__global__ void __launch_bounds__(SK_THREADS) sinkhorn_kernel(const float* __restrict__ cv, int w, int pos, int iters,
+                                                               float* __restrict__ disp, float* __restrict__ conf,
+                                                               float* __restrict__ occ, int* __restrict__ amax) {
+  extern __shared__ float sh[];
+  const int W1 = w + 1;
+  float* u = sh;                 // [W1]
+  float* v = sh + W1;            // [W1]
+  float* red_m = v + W1;         // [SK_WARPS][32]
+  float* red_s = red_m + SK_WARPS * 32;
+  const long long line = blockIdx.x;
+  const float* A = cv + line * (long long)w * w;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float log_m_in = logf(1.0f / (2.0f * (float)w));            // log(1/(2w))   (submodules.py:187-189)
+  const float log_m_dust = logf((float)w / (2.0f * (float)w));       // log(w/(2w))
+  const float log_const = logf(2.0f * (float)w);                      // submodules.py:198-199
+
+  for (int i = threadIdx.x; i < W1; i += SK_THREADS) { u[i] = 0.f; v[i] = 0.f; }
+  __syncthreads();
+
+  // column pass: v[j] = log_nu[j] - LSE_i (A(i,j) + u[i])
+  auto col_pass = [&](bool use_u) {
+    for (int jc = 0; jc < W1; jc += 32) {
+      const int j = jc + lane;
+      float m = -1e30f, s = 0.f;
+      if (j < W1) {
+        for (int i = wid; i < W1; i += SK_WARPS) {
+          float a = (i < w) ? sk_a(A + (long long)i * w, i, j, w, pos) : 0.f;
+          if (use_u) a += u[i];
+          if (a > m) { s = s * expf(m - a) + 1.f; m = a; }
+          else s += expf(a - m);
+        }
+      }
+      red_m[wid * 32 + lane] = m;
+      red_s[wid * 32 + lane] = s;
+      __syncthreads();
+      if (wid == 0 && j < W1) {
+        float M = red_m[lane];
+#pragma unroll
+        for (int k = 1; k < SK_WARPS; ++k) M = fmaxf(M, red_m[k * 32 + lane]);
+        float S = 0.f;
+#pragma unroll
+        for (int k = 0; k < SK_WARPS; ++k) S += red_s[k * 32 + lane] * expf(red_m[k * 32 + lane] - M);
+        float lse = M + logf(fmaxf(S, 1e-30f));
+        v[j] = (j < w ? log_m_in : log_m_dust) - lse;
+      }
+      __syncthreads();
+    }
+  };
+  // row pass: u[i] = log_mu[i] - LSE_j (A(i,j) + v[j])
+  auto row_pass = [&]() {
+    for (int i = wid; i < W1; i += SK_WARPS) {
+      const float* row = A + (long long)i * w;
+      float m = -1e30f;
+      for (int j = lane; j < W1; j += 32) {
+        float a = ((i < w) ? sk_a(row, i, j, w, pos) : 0.f) + v[j];
+        m = fmaxf(m, a);
+      }
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < W1; j += 32) {
+        float a = ((i < w) ? sk_a(row, i, j, w, pos) : 0.f) + v[j];
+        s += expf(a - m);
+      }
+      s = warp_sum(s);
+      if (lane == 0) u[i] = (i < w ? log_m_in : log_m_dust) - (m + logf(fmaxf(s, 1e-30f)));
+    }
+    __syncthreads();
+  };
+
+  col_pass(false);
+  row_pass();
+  for (int it = 1; it < iters; ++it) {
+    col_pass(true);
+    row_pass();
+  }
+
+  // final: prob, row sum (occ), argmax, 5-tap window
+  for (int i = wid; i < w; i += SK_WARPS) {
+    const float* row = A + (long long)i * w;
+    const float ui = u[i] + log_const;
+    float best = -1.f, sum = 0.f;
+    int bidx = 0x7fffffff;
+    const int jend = pos ? i + 1 : w;  // masked entries are exactly 0 (submodules.py:223)
+    for (int j = lane; j < w; j += 32) {
+      float pj = (j < jend) ? expf(row[j] + ui + v[j]) : 0.f;
+      sum += pj;
+      if (pj > best) { best = pj; bidx = j; }
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    // 5 taps around the arg-max, zero outside [0, w)  (submodules.py:228-236)
+    float tap = 0.f;
+    {
+      int j = bidx - 2 + lane;
+      if (lane < 5 && j >= 0 && j < jend) tap = expf(row[j] + ui + v[j]);
+    }
+    float cf = 0.f, cr = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float wk = __shfl_sync(0xffffffffu, tap, k);
+      cf += wk;
+      cr += wk * (float)(bidx + k - 2);
+    }
+    if (lane == 0) {
+      cr = (cr + 1e-4f) / (cf + 1e-4f);
+      long long o = line * w + i;
+      disp[o] = (float)i - cr;
+      conf[o] = cf;
+      occ[o] = sum;
+      amax[o] = bidx;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cost-volume lookup: 9 taps on the row cv[b,y,x,:] at x-disp+dx and 9 on the width-pooled row
+// ------------------------------------------------------------------------------------------------
+__global__ void cv_lookup_kernel(const float* __restrict__ cv, const float* __restrict__ disp, long long npix, int w,
+                                 float* __restrict__ out) {
+  const long long total = npix * 18;
+  const int w2 = w / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / 18;
+    int t = (int)(i - pix * 18);
+    int x = (int)(pix % w);
+    const float* row = cv + pix * w;
+    float d = disp[pix];
+    float r;
+    if (t < 9) {
+      float pos = (float)x - d + (float)(t - 4);
+      float p0 = floorf(pos);
+      float f = pos - p0;
+      int i0 = (int)p0, i1 = i0 + 1;
+      float v0 = (i0 >= 0 && i0 < w) ? row[i0] : 0.f;
+      float v1 = (i1 >= 0 && i1 < w) ? row[i1] : 0.f;
+      r = (1.f - f) * v0 + f * v1;
+    } else {
+      float pos = (float)x / 2.f - d / 2.f + (float)(t - 13);
+      float p0 = floorf(pos);
+      float f = pos - p0;
+      int i0 = (int)p0, i1 = i0 + 1;
+      float v0 = (i0 >= 0 && i0 < w2) ? (row[2 * i0] + row[2 * i0 + 1]) * 0.5f : 0.f;
+      float v1 = (i1 >= 0 && i1 < w2) ? (row[2 * i1] + row[2 * i1 + 1]) * 0.5f : 0.f;
+      r = (1.f - f) * v0 + f * v1;
+    }
+    out[i] = r / 16.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// convex upsampling
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax9(const float* __restrict__ l, float* wt) {
+  float m = l[0];
+#pragma unroll
+  for (int k = 1; k < 9; ++k) m = fmaxf(m, l[k]);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { wt[k] = expf(l[k] - m); s += wt[k]; }
+  float inv = 1.f / s;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wt[k] *= inv;
+}
+
+__global__ void upsample4x_kernel(const float* __restrict__ disp, const float* __restrict__ occ, const float* __restrict__ conf,
+                                  const float* __restrict__ logits, int B, int h, int w, float4* __restrict__ up) {
+  const int H = 4 * h, W = 4 * w;
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W);
+    long long t = i / W;
+    int Y = (int)(t % H);
+    long long b = t / H;
+    float wt[9];
+    softmax9(logits + i * 9, wt);
+    int cy = Y >> 2, cx = X >> 2;
+    float d = 0.f, o = 0.f, c = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = min(max(cy + dy, 0), h - 1), xx = min(max(cx + dx, 0), w - 1);
+        long long q = (b * h + yy) * w + xx;
+        float wk = wt[(dy + 1) * 3 + dx + 1];
+        d += (disp[q] * 4.f) * wk;
+        o += occ[q] * wk;
+        c += conf[q] * wk;
+      }
+    up[i] = make_float4(d, o, c, 0.f);
+  }
+}
+
+__global__ void filter1x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int B, int H, int W,
+                                float* __restrict__ out) {
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W);
+    long long t = i / W;
+    int Y = (int)(t % H);
+    long long b = t / H;
+    float wt[9];
+    softmax9(logits + i * 9, wt);
+    float d = 0.f, o = 0.f, c = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = min(max(Y + dy, 0), H - 1), xx = min(max(X + dx, 0), W - 1);
+        float4 v = up[(b * H + yy) * W + xx];
+        float wk = wt[(dy + 1) * 3 + dx + 1];
+        d += v.x * wk;
+        o += v.y * wk;
+        c += v.z * wk;
+      }
+    out[i] = d;
+    out[total + i] = o;
+    out[2 * total + i] = c;
+  }
+}
+
+}  // namespace s2m2
+
+using namespace s2m2;
+
+extern "C" {
+
+int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t w, float* disp, float* conf, float* occ,
+                                 int32_t* amax, int32_t use_positivity, int32_t iters, void* stream) {
+  S2M2_CHECK(w >= 8 && w <= 8192 && iters >= 1, "sinkhorn: bad w=%d / iters=%d", w, iters);
+  size_t smem = sizeof(float) * (2 * (w + 1) + 2 * SK_WARPS * 32);
+  sinkhorn_kernel<<<B * h, SK_THREADS, smem, (cudaStream_t)stream>>>(cv, w, use_positivity, iters, disp, conf, occ, amax);
+  S2M2_LAUNCH_OK("sinkhorn_softargmax");
+  return 0;
+}
+
+int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h, int32_t w, float* out, void* stream) {
+  long long n = (long long)B * h * w;
+  long long g = (n * 18 + 255) / 256;
+  cv_lookup_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(cv, disp, n, w, out);
+  S2M2_LAUNCH_OK("cv_lookup");
+  return 0;
+}
+
+int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits, int32_t B,
+                               int32_t h, int32_t w, float* up, void* stream) {
+  S2M2_CHECK(aligned(up, 16), "upsample4x_convex: up must be 16-byte aligned");
+  long long n = 16LL * B * h * w;
+  long long g = (n + 255) / 256;
+  upsample4x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(disp, occ, conf, logits, B, h, w, (float4*)up);
+  S2M2_LAUNCH_OK("upsample4x_convex");
+  return 0;
+}
+
+int s2m2b200_filter1x(const float* up, const float* logits, int32_t B, int32_t H, int32_t W, float* out, void* stream) {
+  S2M2_CHECK(aligned(up, 16), "filter1x: up must be 16-byte aligned");
+  long long n = (long long)B * H * W;
+  long long g = (n + 255) / 256;
+  filter1x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, B, H, W, out);
+  S2M2_LAUNCH_OK("filter1x");
+  return 0;
+}
+
+}  // extern "C"

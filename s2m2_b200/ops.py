@@ -1,0 +1,277 @@
+"""ctypes binding of the s2m2b200 C-ABI (include/s2m2b200.h) — the op backend used by ``model.S2M2``.
+
+Thin by design: torch is used only for device memory (caching allocator) and the current stream; every
+op is one call into ``libs2m2b200.so`` with raw pointers.  There is deliberately no fallback: if the
+library is missing or there is no CUDA device, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs2m2b200.so")
+
+F32, F16 = 0, 1
+_DT = {torch.float32: F32, torch.float16: F16}
+
+
+class S2m2Tensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("C", C.c_int32), ("ld", C.c_int64)]
+
+
+class S2m2Conv(C.Structure):
+    _fields_ = [("x", S2m2Tensor), ("x2", S2m2Tensor), ("y", S2m2Tensor), ("res", S2m2Tensor),
+                ("w", C.c_void_p), ("w_dtype", C.c_int32), ("bias", C.c_void_p),
+                ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+                ("Cout", C.c_int32), ("act", C.c_int32), ("shuffle2x2", C.c_int32), ("batch", C.c_int32),
+                ("x_bs", C.c_int64), ("w_bs", C.c_int64), ("y_bs", C.c_int64), ("impl", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libs2m2b200.so (built in-tree by ``__graft_entry__.build()`` / ``make -C s2m2_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU / PyTorch fallback for the S2M2 forward)")
+    lib = C.CDLL(LIB_PATH)
+    lib.s2m2b200_last_error.restype = C.c_char_p
+    lib.s2m2b200_version.restype = C.c_char_p
+    lib.s2m2b200_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+EXPORTS = [
+    "s2m2b200_conv2d", "s2m2b200_attention", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
+    "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
+    "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
+    "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
+    "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_last_error",
+    "s2m2b200_version", "s2m2b200_launch_count",
+]
+
+
+def tview(t: torch.Tensor) -> S2m2Tensor:
+    """Describe an NHWC torch view (last-dim stride 1, pixels equally spaced) to the C side."""
+    if t.dim() != 4 or t.dtype not in _DT:
+        raise ValueError(f"expected a 4-D fp32/fp16 NHWC tensor, got {tuple(t.shape)} {t.dtype}")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    ld = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+    ok = (sc == 1 or c == 1) and (w == 1 or sw == ld) and (h == 1 or sh == w * ld) and (n == 1 or sn == h * w * ld)
+    if not ok:
+        raise ValueError(f"tensor view is not a strided-NHWC view: shape {tuple(t.shape)} strides {t.stride()}")
+    return S2m2Tensor(t.data_ptr(), _DT[t.dtype], n, h, w, c, ld)
+
+
+_NULL_T = S2m2Tensor(None, 0, 0, 0, 0, 0, 0)
+
+
+class CudaOps:
+    """The product's op backend: every method enqueues hand-written CUDA kernels on the current stream."""
+
+    def __init__(self, conv_impl: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("s2m2_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
+        self._pe = {}
+        self._gn_work = {}
+
+    # -- helpers
+    def _chk(self, rc, name):
+        if rc != 0:
+            raise RuntimeError(f"{name} failed ({rc}): {self.lib.s2m2b200_last_error().decode()}")
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.s2m2b200_launch_count())
+
+    def empty(self, shape, dtype, device):
+        return torch.empty(shape, dtype=dtype, device=device)
+
+    def zeros(self, shape, dtype, device):
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+    def pe_tables(self, h, w, device):
+        key = (h, w, str(device))
+        if key not in self._pe:
+            tabs = []
+            for n in (w, h):
+                host = torch.empty((2 * n + 1, 16), dtype=torch.float32)
+                self._chk(self.lib.s2m2b200_pe_table(n, C.c_void_p(host.data_ptr())), "pe_table")
+                tabs.append(host.to(device))
+            self._pe[key] = (tabs[0], tabs[1], h, w)
+        return self._pe[key]
+
+    # -- GEMM-class
+    def conv2d(self, x, cw, act, out, res=None, x2=None, batch=1, x_bs=0, w_bs=0, y_bs=0):
+        a = S2m2Conv()
+        a.x = tview(x)
+        a.x2 = tview(x2) if x2 is not None else _NULL_T
+        a.y = tview(out)
+        a.res = tview(res) if res is not None else _NULL_T
+        cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
+        if cin != cw.cin:
+            raise ValueError(f"conv {cw.name}: input has {cin} channels, weights expect {cw.cin}")
+        a.w = cw.w.data_ptr()
+        a.w_dtype = _DT[cw.w.dtype]
+        a.bias = cw.b.data_ptr() if cw.b is not None else None
+        a.KH, a.KW, a.stride, a.pad_h, a.pad_w = cw.kh, cw.kw, cw.stride, cw.ph, cw.pw
+        a.Cout, a.act, a.shuffle2x2 = cw.cout, act, 1 if cw.shuffle else 0
+        a.batch, a.x_bs, a.w_bs, a.y_bs = batch, x_bs, w_bs, y_bs
+        a.impl = self.conv_impl
+        self._chk(self.lib.s2m2b200_conv2d(C.byref(a), self._stream()), f"conv2d[{cw.name}]")
+
+    def row_corr(self, f, cv):
+        """cv[b,y,i,j] = <f[b,y,i,:], f[B+b,y,j,:]>: one GEMM per scan-line (batched), fp32 (submodules.py:216-217)."""
+        B, h, w, _ = cv.shape
+        Cc = f.shape[3]
+        if f.dtype != torch.float32 or not f.is_contiguous() or not cv.is_contiguous():
+            raise ValueError("row_corr expects contiguous fp32 features / cost volume")
+        a = S2m2Conv()
+        a.x = S2m2Tensor(f.data_ptr(), F32, 1, 1, w, Cc, Cc)
+        a.x2 = _NULL_T
+        a.res = _NULL_T
+        a.y = S2m2Tensor(cv.data_ptr(), F32, 1, 1, w, w, w)
+        a.w = f[B:].data_ptr()
+        a.w_dtype = F32
+        a.bias = None
+        a.KH = a.KW = a.stride = 1
+        a.pad_h = a.pad_w = 0
+        a.Cout, a.act, a.shuffle2x2 = w, 0, 0
+        a.batch, a.x_bs, a.w_bs, a.y_bs = B * h, w * Cc, w * Cc, w * w
+        a.impl = 1
+        self._chk(self.lib.s2m2b200_conv2d(C.byref(a), self._stream()), "row_corr")
+
+    def attention(self, qkv, o, S, N, heads, kv_shift, pe=None, pesum=None):
+        q = tview(qkv)
+        ot = tview(o)
+        if pesum is not None:
+            px, py, ph, pw = pe
+            ps = S2m2Tensor(pesum.data_ptr(), _DT[pesum.dtype], 1, 1, S * N * heads, 32, 32)
+            rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, C.c_void_p(px.data_ptr()),
+                                             C.c_void_p(py.data_ptr()), ph, pw, C.byref(ps), self._stream())
+        else:
+            rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, None, None, 0, 0, None,
+                                             self._stream())
+        self._chk(rc, "attention")
+
+    # -- norms / resampling / element-wise
+    def layernorm(self, x, out, gamma=None, beta=None):
+        g = C.c_void_p(gamma.data_ptr()) if gamma is not None else None
+        b = C.c_void_p(beta.data_ptr()) if beta is not None else None
+        xt, yt = tview(x), tview(out)
+        self._chk(self.lib.s2m2b200_layernorm(C.byref(xt), C.byref(yt), g, b, self._stream()), "layernorm")
+
+    def groupnorm(self, x, groups, gamma, beta, out):
+        key = (x.shape[0], groups, str(x.device))
+        if key not in self._gn_work:
+            self._gn_work[key] = torch.zeros(2 * x.shape[0] * groups, dtype=torch.float64, device=x.device)
+        work = self._gn_work[key]
+        xt, yt = tview(x), tview(out)
+        self._chk(self.lib.s2m2b200_groupnorm(C.byref(xt), C.byref(yt), groups, C.c_void_p(gamma.data_ptr()),
+                                              C.c_void_p(beta.data_ptr()), C.c_void_p(work.data_ptr()), self._stream()),
+                  "groupnorm")
+
+    def _two(self, fn, name, x, y, *extra):
+        xt, yt = tview(x), tview(y)
+        self._chk(fn(C.byref(xt), C.byref(yt), *extra, self._stream()), name)
+
+    def avgpool2(self, x, out):
+        self._two(self.lib.s2m2b200_avgpool2, "avgpool2", x, out)
+
+    def upsample2x(self, x, out):
+        self._two(self.lib.s2m2b200_upsample2x, "upsample2x", x, out)
+
+    def copy_channels(self, src, dst):
+        self._two(self.lib.s2m2b200_copy_channels, "copy_channels", src, dst)
+
+    def unary(self, x, out, act):
+        self._two(self.lib.s2m2b200_unary, "unary", x, out, C.c_int32(act))
+
+    def gate_blend(self, f, g, z0, z1, out):
+        ts = [tview(t) for t in (f, g, z0, z1, out)]
+        self._chk(self.lib.s2m2b200_gate_blend(*[C.byref(t) for t in ts], self._stream()), "gate_blend")
+
+    def mul(self, a, b, out):
+        ts = [tview(t) for t in (a, b, out)]
+        self._chk(self.lib.s2m2b200_mul(*[C.byref(t) for t in ts], self._stream()), "mul")
+
+    def gru_update(self, z, q, h):
+        ts = [tview(t) for t in (z, q, h)]
+        self._chk(self.lib.s2m2b200_gru_update(*[C.byref(t) for t in ts], self._stream()), "gru_update")
+
+    def preprocess(self, left, right, out):
+        B, _, H, W = left.shape
+        ot = tview(out)
+        self._chk(self.lib.s2m2b200_preprocess(C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()), B, H, W,
+                                               C.byref(ot), self._stream()), "preprocess")
+
+    # -- matching
+    def sinkhorn_softargmax(self, cv, disp, conf, occ, amax, use_positivity, iters):
+        B, h, w, _ = cv.shape
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_sinkhorn_softargmax(p(cv), B, h, w, p(disp), p(conf), p(occ), p(amax),
+                                                        int(use_positivity), iters, self._stream()), "sinkhorn_softargmax")
+
+    def cv_lookup(self, cv, disp, out):
+        B, h, w, _ = cv.shape
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_cv_lookup(p(cv), p(disp), B, h, w, p(out), self._stream()), "cv_lookup")
+
+    # -- refiner glue
+    def global_refiner_prep(self, disp, conf, out):
+        ot = tview(out)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_global_refiner_prep(p(disp), p(conf), C.c_int64(disp.numel()), C.byref(ot),
+                                                        self._stream()), "global_refiner_prep")
+
+    def global_refiner_merge(self, disp, conf, upd, use_positivity):
+        if upd.dtype != torch.float32 or not upd.is_contiguous():
+            raise ValueError("global_refiner_merge: update must be contiguous fp32")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_global_refiner_merge(p(disp), p(conf), p(upd), C.c_int64(disp.numel()),
+                                                         int(use_positivity), self._stream()), "global_refiner_merge")
+
+    def local_refiner_prep(self, disp, conf, occ, small):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_local_refiner_prep(p(disp), p(conf), p(occ), C.c_int64(disp.numel()), p(small),
+                                                       self._stream()), "local_refiner_prep")
+
+    def local_refiner_update(self, disp, conf, occ, small, dd, co, use_positivity):
+        B, h, w = disp.shape
+        for t in (dd, co):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("local_refiner_update: head outputs must be contiguous fp32")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_local_refiner_update(p(disp), p(conf), p(occ), p(small), p(dd), p(co), B, h, w,
+                                                         int(use_positivity), self._stream()), "local_refiner_update")
+
+    # -- upsampling
+    def upsample4x_convex(self, disp, occ, conf, logits, up):
+        B, h, w = disp.shape
+        if logits.dtype != torch.float32 or not logits.is_contiguous():
+            raise ValueError("upsample4x_convex: logits must be contiguous fp32 (B,4h,4w,9)")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_upsample4x_convex(p(disp), p(occ), p(conf), p(logits), B, h, w, p(up),
+                                                      self._stream()), "upsample4x_convex")
+
+    def filter1x(self, up, logits, out):
+        B, H, W, _ = up.shape
+        if logits.dtype != torch.float32 or not logits.is_contiguous():
+            raise ValueError("filter1x: logits must be contiguous fp32 (B,H,W,9)")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), B, H, W, p(out), self._stream()), "filter1x")

@@ -1,0 +1,313 @@
+"""Each CUDA kernel (through the C-ABI) vs the plain-torch restatement of the same op (tests/torch_ops.py).
+
+Integer results (arg-max index) must be identical; floating-point results within the stated tolerance.
+"""
+import math
+
+import pytest
+import torch
+
+from s2m2_b200.model import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ConvW
+from torch_ops import TorchOps
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from s2m2_b200.ops import CudaOps
+    return CudaOps(), TorchOps()
+
+
+def _rand(shape, dtype, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cpu") * scale).to(DEV).to(dtype)
+
+
+def _tol(dtype, k=1):
+    # fp32: summation-order differences over K terms; fp16: output rounding (2^-11 rel) dominates
+    return (2e-5 * max(1.0, math.sqrt(k) / 8), 1e-5) if dtype == torch.float32 else (6e-3, 6e-3)
+
+
+def _close(a, b, rtol, atol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    assert torch.isfinite(a).all(), what
+    assert bool((err <= bound).all()), f"{what}: max err {err.max().item():.3e} (ref max {b.abs().max().item():.3e})"
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, kh, kw, stride, act, res, x2split, shuffle, ld_extra
+    (2, 9, 13, 3, 16, 1, 1, 1, ACT_GELU, False, 0, False, 0),        # stem 1x1, scalar path
+    (2, 12, 20, 16, 64, 5, 5, 2, ACT_GELU, False, 0, False, 0),      # 5x5 stride 2
+    (1, 10, 19, 64, 32, 3, 3, 1, ACT_NONE, True, 0, False, 8),       # 3x3 + residual, strided views
+    (2, 8, 12, 32, 32, 3, 3, 2, ACT_NONE, False, 0, False, 0),       # 3x3 stride 2
+    (2, 6, 10, 64, 96, 1, 1, 1, ACT_GELU, False, 32, False, 0),      # two-source 1x1 (cat)
+    (1, 7, 9, 64, 48, 3, 3, 1, ACT_SIGMOID, False, 32, False, 4),    # two-source 3x3 (feat_fusion_layer)
+    (1, 8, 11, 64, 32, 3, 1, 1, ACT_TANH, False, 0, False, 0),       # GRU 3x1
+    (1, 8, 11, 64, 32, 1, 3, 1, ACT_SIGMOID, False, 0, False, 0),    # GRU 1x3
+    (1, 16, 24, 32, 1, 3, 3, 1, ACT_NONE, False, 0, False, 0),       # head -> 1 channel
+    (1, 16, 24, 32, 2, 3, 3, 1, ACT_NONE, False, 0, False, 0),       # head -> 2 channels
+    (1, 16, 24, 9, 96, 1, 1, 1, ACT_GELU, False, 0, False, 0),       # corr encoder 9 -> 96
+    (1, 16, 24, 1, 96, 3, 3, 1, ACT_GELU, False, 0, False, 3),       # disp encoder from a strided scalar map
+    (2, 5, 7, 32, 4 * 16, 1, 1, 1, ACT_NONE, False, 0, True, 0),     # convT 2x2 s2 (Cr=16)
+    (1, 6, 5, 128, 4 * 9, 1, 1, 1, ACT_NONE, False, 0, True, 0),     # convT 2x2 s2 (Cr=9, scalar scatter)
+    (1, 4, 300, 256, 256, 1, 1, 1, ACT_RELU, True, 0, False, 0),     # wide linear + residual
+    (1, 1, 50, 40, 24, 1, 1, 1, ACT_NONE, False, 0, False, 0),       # Cout not multiple of tile
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(ops, case, dtype):
+    cu, th = ops
+    N, H, W, Cin, Cout, kh, kw, stride, act, use_res, split, shuffle, ldx = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    ph, pw = kh // 2, kw // 2
+    K = kh * kw * Cin
+    w = _rand((Cout, K), dtype, g, 1.0 / math.sqrt(K))
+    b = _rand((Cout,), torch.float32, g, 0.5)
+    cw = ConvW(w, b, kh, kw, stride, ph, pw, Cin, Cout, shuffle, "t")
+    C1 = Cin - split if split else Cin
+    xbuf = _rand((N, H, W, C1 + ldx), dtype, g)
+    x = xbuf[..., :C1] if ldx else xbuf
+    x2 = _rand((N, H, W, split), dtype, g) if split else None
+    Ho, Wo = (H + 2 * ph - kh) // stride + 1, (W + 2 * pw - kw) // stride + 1
+    oshape = (N, 2 * Ho, 2 * Wo, Cout // 4) if shuffle else (N, Ho, Wo, Cout)
+    res = _rand(oshape, dtype, g) if use_res else None
+    out_a = torch.zeros(oshape[:3] + (oshape[3] + ldx,), dtype=dtype, device=DEV)[..., :oshape[3]] if ldx % 4 == 0 and ldx else \
+        torch.zeros(oshape, dtype=dtype, device=DEV)
+    out_b = torch.zeros(oshape, dtype=dtype, device=DEV)
+    cu.conv2d(x, cw, act, out_a, res, x2)
+    th.conv2d(x, cw, act, out_b, res, x2)
+    torch.cuda.synchronize()
+    rt, at = _tol(dtype, K)
+    _close(out_a, out_b, rt, at * 4, f"conv {case}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_conv2d_mixed_dtypes_and_inplace_residual(ops, dtype):
+    """fp32 scalar-map input with activation-dtype weights, fp32 output; and out aliasing res (z += f(z))."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(5)
+    x = _rand((1, 12, 18, 4), torch.float32, g)[..., 1:3]
+    cw = ConvW(_rand((64, 18), dtype, g, 0.3), _rand((64,), torch.float32, g), 3, 3, 1, 1, 1, 2, 64, False, "t")
+    a = torch.zeros((1, 12, 18, 64), dtype=torch.float32, device=DEV)
+    b = torch.zeros_like(a)
+    cu.conv2d(x, cw, ACT_GELU, a)
+    th.conv2d(x, cw, ACT_GELU, b)
+    _close(a, b, 1e-4, 1e-4, "mixed")
+    z = _rand((1, 6, 40, 64), dtype, g)
+    cw2 = ConvW(_rand((64, 64), dtype, g, 0.1), None, 1, 1, 1, 0, 0, 64, 64, False, "t")
+    za, zb = z.clone(), z.clone()
+    cu.conv2d(z, cw2, ACT_NONE, za, res=za)
+    th.conv2d(z, cw2, ACT_NONE, zb, res=zb)
+    rt, at = _tol(dtype, 64)
+    _close(za, zb, rt, at * 4, "inplace")
+
+
+def test_row_corr(ops):
+    cu, th = ops
+    g = torch.Generator().manual_seed(1)
+    f = _rand((4, 5, 37, 96), torch.float32, g)
+    a = torch.zeros((2, 5, 37, 37), device=DEV)
+    b = torch.zeros_like(a)
+    cu.row_corr(f, a)
+    th.row_corr(f, b)
+    _close(a, b, 2e-5, 2e-4, "row_corr")
+
+
+ATTN_CASES = [
+    # S, N, heads, d, cross, pe(h,w)
+    (6, 40, 1, 32, False, None),
+    (8, 76, 2, 64, True, None),
+    (4, 33, 4, 16, True, None),
+    (2, 6 * 7, 8, 8, False, (6, 7)),
+    (2, 5 * 9, 8, 32, False, (5, 9)),
+    (2, 100, 8, 4, False, None),
+    (3, 70, 1, 256, False, None),
+    (2, 50, 2, 96, True, None),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention(ops, case, dtype):
+    cu, th = ops
+    S, N, heads, d, cross, pe_hw = case
+    C = heads * d
+    g = torch.Generator().manual_seed(7)
+    qkv = _rand((S, 1, N, 3 * C), dtype, g)
+    oa = torch.zeros((S, 1, N, C), dtype=dtype, device=DEV)
+    ob = torch.zeros_like(oa)
+    pe = pa = pb = None
+    if pe_hw:
+        pe_c, pe_t = cu.pe_tables(pe_hw[0], pe_hw[1], torch.device(DEV)), th.pe_tables(pe_hw[0], pe_hw[1], torch.device(DEV))
+        _close(pe_c[0], pe_t[0], 1e-5, 1e-6, "pe_x table")
+        _close(pe_c[1], pe_t[1], 1e-5, 1e-6, "pe_y table")
+        pa = torch.zeros((S, N, heads, 32), dtype=dtype, device=DEV)
+        pb = torch.zeros_like(pa)
+        pe = pe_c
+    cu.attention(qkv, oa, S, N, heads, S // 2 if cross else 0, pe, pa)
+    th.attention(qkv, ob, S, N, heads, S // 2 if cross else 0, pe, pb)
+    rt, at = (1e-4, 2e-5) if dtype == torch.float32 else (6e-3, 4e-3)
+    _close(oa, ob, rt, at, f"attention {case}")
+    if pe_hw:
+        _close(pa, pb, rt, at, f"pesum {case}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("C", [32, 128, 256, 384, 768])
+def test_layernorm(ops, C, dtype):
+    cu, th = ops
+    g = torch.Generator().manual_seed(2)
+    x = _rand((2, 3, 17, C + 8), dtype, g, 3.0)[..., :C]
+    gamma, beta = _rand((C,), torch.float32, g), _rand((C,), torch.float32, g)
+    for gb in ((None, None), (gamma, beta)):
+        a = torch.zeros((2, 3, 17, C), dtype=dtype, device=DEV)
+        b = torch.zeros_like(a)
+        cu.layernorm(x, a, *gb)
+        th.layernorm(x, b, *gb)
+        _close(a, b, *((2e-5, 2e-5) if dtype == torch.float32 else (4e-3, 4e-3)), "layernorm")
+    a32 = torch.zeros((2, 3, 17, C), dtype=torch.float32, device=DEV)
+    b32 = torch.zeros_like(a32)
+    cu.layernorm(x, a32, gamma, beta)
+    th.layernorm(x, b32, gamma, beta)
+    _close(a32, b32, 2e-5, 2e-5, "layernorm->fp32")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("C", [32, 128, 192])
+def test_groupnorm(ops, C, dtype):
+    cu, th = ops
+    g = torch.Generator().manual_seed(3)
+    x = _rand((2, 30, 44, C), dtype, g, 2.0) + 0.5
+    gamma, beta = _rand((C,), torch.float32, g), _rand((C,), torch.float32, g)
+    a = torch.zeros_like(x)
+    b = torch.zeros_like(x)
+    cu.groupnorm(x, 8, gamma, beta, a)
+    th.groupnorm(x, 8, gamma, beta, b)
+    _close(a, b, *((3e-5, 3e-5) if dtype == torch.float32 else (4e-3, 4e-3)), "groupnorm")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_resample_and_elementwise(ops, dtype):
+    cu, th = ops
+    g = torch.Generator().manual_seed(4)
+    tol = (1e-6, 1e-6) if dtype == torch.float32 else (2e-3, 2e-3)
+    x = _rand((2, 6, 10, 32 + 4), dtype, g)[..., 4:]
+    for fn, shape in (("avgpool2", (2, 3, 5, 32)), ("upsample2x", (2, 12, 20, 32))):
+        a = torch.zeros(shape, dtype=dtype, device=DEV)
+        b = torch.zeros_like(a)
+        getattr(cu, fn)(x, a)
+        getattr(th, fn)(x, b)
+        _close(a, b, *tol, fn)
+    f, gg, z0, z1 = (_rand((2, 6, 10, 32), dtype, g) for _ in range(4))
+    gg = torch.sigmoid(gg.float() * 3).to(dtype)
+    a, b = torch.zeros_like(f), torch.zeros_like(f)
+    cu.gate_blend(f, gg, z0, z1, a)
+    th.gate_blend(f, gg, z0, z1, b)
+    _close(a, b, *tol, "gate_blend")
+    a, b = f.clone(), f.clone()
+    cu.gate_blend(a, gg, z0, z1, a)      # in place on f, as the model does
+    th.gate_blend(b, gg, z0, z1, b)
+    _close(a, b, *tol, "gate_blend in place")
+    for act in (ACT_TANH, ACT_GELU, ACT_SIGMOID, ACT_RELU):
+        a, b = torch.zeros_like(f), torch.zeros_like(f)
+        cu.unary(f, a, act)
+        th.unary(f, b, act)
+        _close(a, b, 2e-6 if dtype == torch.float32 else 2e-3, tol[1], f"unary {act}")
+    a, b = torch.zeros_like(f), torch.zeros_like(f)
+    cu.mul(f, z0, a)
+    th.mul(f, z0, b)
+    _close(a, b, *tol, "mul")
+    ha, hb = z1.clone(), z1.clone()
+    cu.gru_update(gg, f, ha)
+    th.gru_update(gg, f, hb)
+    _close(ha, hb, *tol, "gru_update")
+    wide = torch.zeros((2, 6, 10, 72), dtype=dtype, device=DEV)
+    cu.copy_channels(f, wide[..., 8:40])
+    assert torch.equal(wide[..., 8:40], f) and float(wide[..., :8].abs().sum()) == 0 and float(wide[..., 40:].abs().sum()) == 0
+    l, r = torch.randint(0, 256, (2, 3, 8, 12), generator=g).float().to(DEV), torch.randint(0, 256, (2, 3, 8, 12), generator=g).float().to(DEV)
+    a = torch.zeros((4, 8, 12, 3), dtype=dtype, device=DEV)
+    b = torch.zeros_like(a)
+    cu.preprocess(l, r, a)
+    th.preprocess(l, r, b)
+    _close(a, b, *tol, "preprocess")
+
+
+@pytest.mark.parametrize("pos", [True, False])
+@pytest.mark.parametrize("w", [24, 40, 76, 161])
+def test_sinkhorn_softargmax(ops, w, pos):
+    cu, th = ops
+    g = torch.Generator().manual_seed(w)
+    B, h = 2, 5
+    cv = _rand((B, h, w, w), torch.float32, g, 6.0)
+    outs = []
+    for o in (cu, th):
+        d, c, oc = (torch.zeros((B, h, w), device=DEV) for _ in range(3))
+        am = torch.zeros((B, h, w), dtype=torch.int32, device=DEV)
+        o.sinkhorn_softargmax(cv, d, c, oc, am, pos, 3)
+        outs.append((d, c, oc, am))
+    torch.cuda.synchronize()
+    (d0, c0, o0, a0), (d1, c1, o1, a1) = outs
+    assert torch.equal(a0, a1), f"argmax mismatches: {(a0 != a1).sum().item()}"
+    _close(c0, c1, 1e-4, 1e-6, "conf")
+    _close(o0, o1, 1e-4, 1e-6, "occ")
+    _close(d0, d1, 1e-5, 2e-4, "disp")
+
+
+def test_cv_lookup_and_refiner_glue(ops):
+    cu, th = ops
+    g = torch.Generator().manual_seed(9)
+    B, h, w = 2, 6, 37
+    cv = _rand((B, h, w, w), torch.float32, g, 5.0)
+    disp = (torch.rand((B, h, w), generator=g) * 45 - 4).to(DEV)
+    a, b = torch.zeros((B, h, w, 18), device=DEV), torch.zeros((B, h, w, 18), device=DEV)
+    cu.cv_lookup(cv, disp, a)
+    th.cv_lookup(cv, disp, b)
+    _close(a, b, 1e-5, 2e-5, "cv_lookup")
+    conf = torch.rand((B, h, w), generator=g).to(DEV)
+    occ = torch.rand((B, h, w), generator=g).to(DEV)
+    for dtype in (torch.float32, torch.float16):
+        oa = torch.zeros((B, h, w, 40), dtype=dtype, device=DEV)
+        ob = torch.zeros_like(oa)
+        cu.global_refiner_prep(disp, conf, oa[..., 32:34])
+        th.global_refiner_prep(disp, conf, ob[..., 32:34])
+        _close(oa, ob, 1e-5 if dtype == torch.float32 else 2e-3, 1e-6 if dtype == torch.float32 else 2e-3, "gr_prep")
+    upd = _rand((B, h, w, 1), torch.float32, g, 10.0)
+    da, db = disp.clone(), disp.clone()
+    cu.global_refiner_merge(da, conf, upd, True)
+    th.global_refiner_merge(db, conf, upd, True)
+    _close(da, db, 0, 1e-6, "gr_merge")
+    sa, sb = torch.zeros((B, h, w, 4), device=DEV), torch.zeros((B, h, w, 4), device=DEV)
+    cu.local_refiner_prep(disp, conf, occ, sa)
+    th.local_refiner_prep(disp, conf, occ, sb)
+    _close(sa, sb, 2e-6, 2e-6, "lr_prep")
+    dd, co = _rand((B, h, w, 1), torch.float32, g), _rand((B, h, w, 2), torch.float32, g)
+    xa = [t.clone() for t in (disp, conf, occ)]
+    xb = [t.clone() for t in (disp, conf, occ)]
+    cu.local_refiner_update(*xa, sa, dd, co, True)
+    th.local_refiner_update(*xb, sb, dd, co, True)
+    for u, v, nm in zip(xa, xb, ("disp", "conf", "occ")):
+        _close(u, v, 2e-6, 2e-6, "lr_update " + nm)
+    # the occlusion mask (s2m2.py:179) is a hard decision: identical zero pattern
+    assert torch.equal(xa[2] == 0, xb[2] == 0)
+
+
+def test_convex_upsampling(ops):
+    cu, th = ops
+    g = torch.Generator().manual_seed(10)
+    B, h, w = 2, 5, 7
+    disp, occ, conf = (torch.rand((B, h, w), generator=g).to(DEV) * s for s in (30, 1, 1))
+    logits = _rand((B, 4 * h, 4 * w, 9), torch.float32, g, 2.0)
+    ua, ub = torch.zeros((B, 4 * h, 4 * w, 4), device=DEV), torch.zeros((B, 4 * h, 4 * w, 4), device=DEV)
+    cu.upsample4x_convex(disp, occ, conf, logits, ua)
+    th.upsample4x_convex(disp, occ, conf, logits, ub)
+    _close(ua, ub, 2e-6, 2e-5, "upsample4x")
+    l1 = _rand((B, 4 * h, 4 * w, 9), torch.float32, g, 2.0)
+    oa, ob = torch.zeros((3, B, 1, 4 * h, 4 * w), device=DEV), torch.zeros((3, B, 1, 4 * h, 4 * w), device=DEV)
+    cu.filter1x(ub, l1, oa)
+    th.filter1x(ub, l1, ob)
+    _close(oa, ob, 2e-6, 2e-5, "filter1x")

@@ -1,0 +1,131 @@
+"""End-to-end parity of the CUDA path (through the nn.Module surface / C-ABI) against
+  (a) golden vectors produced by the real reference (tests/golden, oracle/make_golden.py),
+  (b) the oracle restatement run on the same seeded inputs (on the GPU in fp32 with TF32 disabled for the
+      larger sizes so that it finishes in seconds),
+  (c) size-independent properties at the BASELINE sizes.
+Tolerances: fp32 mode — EPE < 1e-3 px (north_star), arg-max index identical; fp16 mode — the reference's own
+autocast-fp16 yard-stick (EPE 7e-3, l_inf 0.63 px) with head-room, stated per test.
+"""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from oracle import s2m2_oracle as O
+from s2m2_b200.model import S2M2
+from s2m2_b200.weights import random_state_dict, synthetic_pair
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(C, NTR, sd, pos=True, it=3, precision="fp32"):
+    m = S2M2(C, 1, NTR, use_positivity=pos, refine_iter=it, precision=precision).eval()
+    m.my_load_state_dict(sd)
+    return m.to(DEV)
+
+
+def _oracle_gpu(sd, left, right, NTR, pos, it, taps=None):
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sdg = {k: v.to(DEV) for k, v in sd.items()}
+        return O.forward(sdg, left.to(DEV), right.to(DEV), NTR, pos, it, taps)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp32_path_matches_reference_golden(name):
+    cfg, g = load_golden(name)
+    sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
+    m = _model(cfg["C"], cfg["NTR"], sd, cfg["pos"], cfg["it"], "fp32")
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    m.taps = {}
+    d, o, c = m(left.to(DEV), right.to(DEV))
+    torch.cuda.synchronize()
+    d, o, c = d.cpu(), o.cpu(), c.cpu()
+    assert d.shape == g["disp"].shape
+    epe = (d - g["disp"]).abs().mean().item()
+    print(f"{name}: EPE {epe:.3e} max {(d - g['disp']).abs().max().item():.3e}")
+    assert epe < 1e-3
+    assert (d - g["disp"]).abs().max() < 2e-2
+    assert (o - g["occ"]).abs().max() < 2e-3
+    assert (c - g["conf"]).abs().max() < 2e-3
+    assert (m.taps["disp_init.cv"].cpu() - g["tap:disp_init#0.3"]).abs().max() < 5e-3
+    assert (m.taps["disp_init.disp"].cpu() - g["tap:disp_init#0.0"]).abs().max() < 2e-3
+
+
+def test_fp32_argmax_and_masks_bit_exact_vs_oracle():
+    """prob_max_ind (submodules.py:226), conf>.2 (refinenet.py:65) and x-disp>=0 (s2m2.py:179) decisions."""
+    C, NTR, H, W = 64, 1, 128, 192
+    sd = random_state_dict(C, NTR, 21)
+    left, right = synthetic_pair(1, H, W, 22)
+    m = _model(C, NTR, sd)
+    m.taps = {}
+    m(left.to(DEV), right.to(DEV))
+    ot = {}
+    _oracle_gpu(sd, left, right, NTR, True, 3, ot)
+    assert torch.equal(m.taps["disp_init.argmax"], ot["disp_init.argmax"])
+    assert torch.equal(m.taps["disp_init.conf"] > 0.2, ot["disp_init.conf"] > 0.2)
+    for it in range(3):
+        mine = m.taps[f"refiner.{it}.occ"] == 0
+        ref = ot[f"refiner.{it}.occ"] == 0
+        assert int((mine != ref).sum()) == 0, f"occ mask differs at iteration {it}"
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES[:2] + GOLDEN_CASES[3:])
+def test_fp16_path_close_to_reference_golden(name):
+    cfg, g = load_golden(name)
+    sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
+    m = _model(cfg["C"], cfg["NTR"], sd, cfg["pos"], cfg["it"], "fp16")
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    d, o, c = (t.cpu() for t in m(left.to(DEV), right.to(DEV)))
+    epe = (d - g["disp"]).abs().mean().item()
+    print(f"{name} fp16: EPE {epe:.3e} max {(d - g['disp']).abs().max().item():.3e}")
+    scale = max(1.0, g["disp"].abs().max().item() / 4)
+    assert torch.isfinite(d).all() and torch.isfinite(o).all() and torch.isfinite(c).all()
+    assert epe < 5e-2 * scale                      # reference autocast-fp16 itself: 7e-3
+    assert (o - g["occ"]).abs().mean() < 2e-2 and (c - g["conf"]).abs().mean() < 2e-2
+
+
+def test_s_640x480_vs_oracle_on_gpu():
+    """BASELINE config 2 (S, 640x480): fp32 CUDA path vs the oracle (fp32, TF32 off) on identical inputs."""
+    C, NTR = 128, 1
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, 480, 640, 1)
+    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3)]
+    m = _model(C, NTR, sd)
+    out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+    epe = (out[0] - ref[0]).abs().mean().item()
+    print(f"S 640x480 fp32: EPE {epe:.3e} max {(out[0] - ref[0]).abs().max().item():.3e}")
+    assert epe < 1e-3
+    assert (out[1] - ref[1]).abs().mean() < 1e-3 and (out[2] - ref[2]).abs().mean() < 1e-3
+    m16 = _model(C, NTR, sd, precision="fp16")
+    out16 = [t.cpu() for t in m16(left.to(DEV), right.to(DEV))]
+    epe16 = (out16[0] - ref[0]).abs().mean().item()
+    print(f"S 640x480 fp16: EPE {epe16:.3e} max {(out16[0] - ref[0]).abs().max().item():.3e}")
+    assert epe16 < 5e-2
+
+
+def test_batch_independence_and_determinism():
+    """Pairs are independent units: a batch of two identical pairs gives two identical results,
+    equal to the single-pair result, and repeated calls are bit-identical."""
+    C, NTR = 32, 1
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, 64, 96, 1)
+    m = _model(C, NTR, sd, precision="fp16")
+    l2, r2 = torch.cat([left, left]).to(DEV), torch.cat([right, right]).to(DEV)
+    a = m(l2, r2)
+    b = m(l2, r2)
+    s = m(left.to(DEV), right.to(DEV))
+    for x, y, z in zip(a, b, s):
+        assert torch.equal(x, y)
+        assert torch.equal(x[0], x[1])
+        assert (x[0] - z[0]).abs().max() < 1e-3
+
+
+def test_rejects_bad_shapes_loudly():
+    m = _model(32, 1, random_state_dict(32, 1, 0))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 60, 64, device=DEV), torch.zeros(1, 3, 60, 64, device=DEV))
