@@ -1,6 +1,393 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the TMA/TMEM kernel lands in this file).
+// tcgen05 implicit-GEMM convolution for sm_100a: fp16 operands, fp32 accumulation in TMEM.
+//
+//   D[128 pixels x BN couts] += A[128 x 64] * B[BN x 64]^T   per k-block (64 input channels of one filter tap)
+//
+//   * A (activations, NHWC): one TMA box {64 ch, tw, th, 1 img} of the input at the tap's spatial offset — TMA's
+//     out-of-bounds zero fill IS the convolution's zero padding, so there is no im2col and no border code.
+//     The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = the canonical K-major
+//     UMMA layout.  conv over cat([x, x2]) walks two tensor maps (no concat buffer).
+//   * B (weights, [Cout][taps*Cin] K-major): TMA box {64, BN}.
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//     (tcgen05.ld -> bias/activation/residual -> 16/32-byte global stores, optional ConvTranspose2x2 scatter).
+//   * smem ring of STAGES k-blocks guarded by full/empty mbarriers; tcgen05.commit releases slots.
+//
+// Reference ops replaced: the big nn.Conv2d / nn.Linear / ConvTranspose2d(k=2) layers (include/s2m2b200.h).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
+
 namespace s2m2 {
-int conv_tc_supported(const S2m2Conv* a) { (void)a; return 0; }
-int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) { (void)a; (void)s; set_error("tcgen05 conv not built"); return -1; }
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr unsigned long long TC_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
+
+struct TcP {
+  const float* bias;
+  const void* res;
+  void* y;
+  long long res_ld, y_ld;
+  int rh, yh;            // residual / output fp16 flags
+  int flat;              // 1x1 conv: pixels are one flat dimension
+  int Ho, Wo, Cout;      // output geometry (for flat: Wo = total pixels, Ho = 1)
+  int tw, th, tiles_x, tiles_y;
+  int KW, ph, pw, taps;
+  int cpb1, cpb2;        // 64-channel chunks per tap from x and x2
+  int act, shuffle, Cr;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
+      printf("s2m2b200 conv_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                                 const __grid_constant__ CUtensorMap tmx2,
+                                                                 const __grid_constant__ CUtensorMap tmw, const TcP p) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + STAGES * B_BYTES);  // full[STAGES], empty[STAGES], tmem_full
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+  // ---- tile coordinates
+  const int n0 = blockIdx.y * BN;
+  int img = 0, x0 = 0, y0 = 0;
+  if (p.flat) {
+    x0 = blockIdx.x * TC_BM;
+  } else {
+    int mt = blockIdx.x;
+    int txi = mt % p.tiles_x;
+    int t = mt / p.tiles_x;
+    int tyi = t % p.tiles_y;
+    img = t / p.tiles_y;
+    x0 = txi * p.tw;
+    y0 = tyi * p.th;
+  }
+  const int cpb = p.cpb1 + p.cpb2;
+  const int nkb = p.taps * cpb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+        const int tap = kb / cpb, ch = kb - tap * cpb;
+        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + s * B_BYTES);
+        if (ch < p.cpb1) tma_load_4d(&tmx, dstA, full0 + 8 * s, ch * TC_BK, x0 + kx - p.pw, y0 + ky - p.ph, img);
+        else tma_load_4d(&tmx2, dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + kx - p.pw, y0 + ky - p.ph, img);
+        tma_load_2d(&tmw, dstB, full0 + 8 * s, kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t ad = make_sdesc(smem_u32(sA + s * A_BYTES)), bd = make_sdesc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)  // +32 B (= 2 in the >>4 encoded start address) per 16-element K step
+          umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(empty0 + 8 * s);            // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tfull);                        // accumulator complete
+    }
+  } else {
+    // ================= epilogue warps (TMEM lanes 32*(warp%4) ..) =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
+    bool valid;
+    long long opix;                              // output pixel index (before shuffle)
+    int py = 0, px = 0;
+    if (p.flat) {
+      valid = x0 + r < p.Wo;
+      opix = x0 + r;
+    } else {
+      py = y0 + r / p.tw;
+      px = x0 + r % p.tw;
+      valid = (r < p.tw * p.th) && py < p.Ho && px < p.Wo;
+      opix = ((long long)img * p.Ho + py) * p.Wo + px;
+    }
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      const int n = n0 + c0;
+      if (n >= p.Cout) break;                    // uniform across the warp
+      uint32_t rr[16];
+      tmem_ld16(trow + c0, rr);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!valid) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float t = __uint_as_float(rr[i]);
+        if (p.bias) t += __ldg(p.bias + n + i);
+        v[i] = act_apply(t, p.act);
+      }
+      long long off;
+      if (p.shuffle) {  // ConvTranspose2d(k=2,s=2) scatter: column = (a*2+b)*Cr + co
+        const int qd = n / p.Cr, co = n - qd * p.Cr;
+        const long long pix = ((long long)img * 2 * p.Ho + 2 * py + (qd >> 1)) * (2 * p.Wo) + 2 * px + (qd & 1);
+        off = pix * p.y_ld + co;
+      } else {
+        off = opix * p.y_ld + n;
+        if (p.res) {
+          const long long ro = opix * p.res_ld + n;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 t = ld4(p.res, ro + i, p.rh);
+            v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+          }
+        }
+      }
+      if (p.yh) {
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        uint4* dst = (uint4*)((__half*)p.y + off);
+        dst[0] = *(uint4*)&h[0];
+        dst[1] = *(uint4*)&h[4];
+      } else {
+        float4* dst = (float4*)((float*)p.y + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)f;
+  }
+  return fn;
+}
+
+static bool tc_device_ok() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    ok = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+          major == 10 && get_encode() != nullptr)
+             ? 1
+             : 0;
+  }
+  return ok == 1;
+}
+
+int conv_tc_supported(const S2m2Conv* a) {
+  const S2m2Tensor &x = a->x, &x2 = a->x2, &y = a->y, &res = a->res;
+  if (x.dtype != S2M2_F16 || a->w_dtype != S2M2_F16) return 0;
+  if (a->stride != 1 || (a->batch > 1)) return 0;
+  if (x.C % TC_BK || x.ld % 8 || !aligned(x.ptr, 16)) return 0;
+  if (x2.ptr && (x2.C % TC_BK || x2.ld % 8 || !aligned(x2.ptr, 16))) return 0;
+  if (!aligned(a->w, 16)) return 0;
+  if (a->Cout % 16 || a->Cout < 64) return 0;
+  // same-size convolutions only (pad = k/2) or 1x1
+  const int Ho = x.H + 2 * a->pad_h - a->KH + 1, Wo = x.W + 2 * a->pad_w - a->KW + 1;
+  if (Ho != x.H || Wo != x.W) return 0;
+  const int ye = y.dtype == S2M2_F16 ? 8 : 4;  // elements per 16 B
+  if (y.ld % ye || !aligned(y.ptr, 16)) return 0;
+  if (a->shuffle2x2) {
+    if ((a->Cout / 4) % 16) return 0;
+  } else if (res.ptr) {
+    if (res.ld % 4 || !aligned(res.ptr, res.dtype == S2M2_F16 ? 8 : 16)) return 0;
+  }
+  if ((long long)x.N * x.H * x.W < 256) return 0;   // tiny problems: launch-bound either way
+  return tc_device_ok() ? 1 : 0;
+}
+
+static int encode_act(CUtensorMap* m, const S2m2Tensor& t, bool flat, int tw, int th) {
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  if (flat) {
+    dims[0] = t.C; dims[1] = (cuuint64_t)t.N * t.H * t.W; dims[2] = 1; dims[3] = 1;
+    strides[0] = (cuuint64_t)t.ld * 2; strides[1] = strides[0] * dims[1]; strides[2] = strides[1];
+    box[0] = TC_BK; box[1] = TC_BM; box[2] = 1; box[3] = 1;
+  } else {
+    dims[0] = t.C; dims[1] = t.W; dims[2] = t.H; dims[3] = t.N;
+    strides[0] = (cuuint64_t)t.ld * 2; strides[1] = strides[0] * t.W; strides[2] = strides[1] * t.H;
+    box[0] = TC_BK; box[1] = tw; box[2] = th; box[3] = 1;
+  }
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const TcP& p, dim3 grid, cudaStream_t s) {
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(mx, mx2, mw, p);
+  S2M2_LAUNCH_OK("conv_tc");
+  return 0;
+}
+
+int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
+  const S2m2Tensor &x = a->x, &x2 = a->x2, &y = a->y, &res = a->res;
+  TcP p{};
+  p.bias = a->bias; p.res = a->shuffle2x2 ? nullptr : res.ptr; p.y = y.ptr;
+  p.res_ld = res.ptr ? res.ld : 0; p.y_ld = y.ld;
+  p.rh = res.ptr ? res.dtype == S2M2_F16 : 0; p.yh = y.dtype == S2M2_F16;
+  p.flat = (a->KH == 1 && a->KW == 1) ? 1 : 0;
+  p.Cout = a->Cout; p.KW = a->KW; p.ph = a->pad_h; p.pw = a->pad_w; p.taps = a->KH * a->KW;
+  p.cpb1 = x.C / TC_BK; p.cpb2 = x2.ptr ? x2.C / TC_BK : 0;
+  p.act = a->act; p.shuffle = a->shuffle2x2; p.Cr = a->shuffle2x2 ? a->Cout / 4 : a->Cout;
+  long long mtiles;
+  if (p.flat && !a->shuffle2x2) {
+    p.Ho = 1; p.Wo = (int)((long long)x.N * x.H * x.W); p.tw = TC_BM; p.th = 1; p.tiles_x = cdiv(p.Wo, TC_BM); p.tiles_y = 1;
+    mtiles = p.tiles_x;
+  } else {
+    p.flat = 0;
+    p.Ho = x.H; p.Wo = x.W;
+    // patch shape: th*tw = 128, minimise padded-tile waste
+    int best_tw = 16;
+    long long best = -1;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+      int th = TC_BM / tw;
+      long long tiles = (long long)cdiv(p.Wo, tw) * cdiv(p.Ho, th);
+      if (best < 0 || tiles < best || (tiles == best && tw > best_tw)) { best = tiles; best_tw = tw; }
+    }
+    p.tw = best_tw; p.th = TC_BM / best_tw;
+    p.tiles_x = cdiv(p.Wo, p.tw); p.tiles_y = cdiv(p.Ho, p.th);
+    mtiles = (long long)p.tiles_x * p.tiles_y * x.N;
+  }
+  CUtensorMap mx, mx2, mw;
+  if (int r = encode_act(&mx, x, p.flat, p.tw, p.th)) return r;
+  if (x2.ptr) {
+    if (int r = encode_act(&mx2, x2, p.flat, p.tw, p.th)) return r;
+  } else {
+    mx2 = mx;
+  }
+  const int BN = a->Cout >= 256 ? 256 : (a->Cout >= 128 ? 128 : 64);
+  {
+    const long long K = (long long)p.taps * (x.C + (x2.ptr ? x2.C : 0));
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Cout}, strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN}, estr[2] = {1, 1};
+    CUresult r = get_encode()(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+  dim3 grid((unsigned)mtiles, cdiv(a->Cout, BN));
+  if (BN == 256) return launch_tc<256, 4>(mx, mx2, mw, p, grid, s);
+  if (BN == 128) return launch_tc<128, 4>(mx, mx2, mw, p, grid, s);
+  return launch_tc<64, 4>(mx, mx2, mw, p, grid, s);
+}
+
 }  // namespace s2m2

@@ -79,10 +79,12 @@ _NULL_T = S2m2Tensor(None, 0, 0, 0, 0, 0, 0)
 class CudaOps:
     """The product's op backend: every method enqueues hand-written CUDA kernels on the current stream."""
 
-    def __init__(self, conv_impl: int = 0):
+    def __init__(self, conv_impl: int = None):
         if not torch.cuda.is_available():
             raise RuntimeError("s2m2_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = load_library()
+        if conv_impl is None:
+            conv_impl = int(os.environ.get("S2M2_CONV_IMPL", "0"))
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
         self._pe = {}
         self._gn_work = {}
