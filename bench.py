@@ -177,15 +177,8 @@ def main():
         model.my_load_state_dict(random_state_dict(C, NTR, 0))
     model = model.to(dev)
     if world > 1:   # the only collective on the path: one flat weight broadcast over NVLink
-        flat = torch.cat([p.data.reshape(-1) for p in model._p.values()])
-        dist.broadcast(flat, 0)
-        off = 0
-        for p in model._p.values():
-            n = p.numel()
-            p.data.copy_(flat[off:off + n].view_as(p))
-            off += n
-        del flat
-        model._packed = None
+        from s2m2_b200.parallel import broadcast_weights
+        broadcast_weights(model, 0)
 
     left_h, right_h = synthetic_pair(B, H, W, 1 + rank)
     left_h, right_h = left_h.pin_memory(), right_h.pin_memory()

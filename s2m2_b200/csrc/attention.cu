@@ -2,22 +2,13 @@
 // tensor-core kernel does not take).  One CTA = 32 queries of one (sequence, head); K/V streamed through shared
 // memory in tiles of 32 keys with an online softmax; optional contextual relative-PE accumulation
 // (attentions.py:42-48) from two tiny tables instead of the (N,N,32) tensor of utils.py:32-60.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "attention.cuh"
 
 namespace s2m2 {
 
 constexpr int AT_BQ = 32, AT_BK = 32, AT_THREADS = 256, AT_QPW = 4;  // 8 warps x 4 queries
-
-struct AttnP {
-  const void* qkv;
-  void* out;
-  void* pesum;
-  const float *pe_x, *pe_y;
-  long long qkv_ld, out_ld;
-  int qh, oh, ph_half;
-  int S, N, heads, d, C, kv_shift, pe_h, pe_w;
-  float scale;
-};
 
 template <int MAXI>  // MAXI = ceil(d / 32)
 __global__ void __launch_bounds__(AT_THREADS) attention_simt_kernel(AttnP p) {
@@ -219,5 +210,7 @@ extern "C" int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, 
   if (p.d % 4 == 0) {
     S2M2_CHECK(qkv->ld % 4 == 0 && aligned(qkv->ptr, 4 * esize(qkv->dtype)), "attention: qkv view must be 4-element aligned");
   }
+  static const int force_simt = getenv("S2M2_ATTN_IMPL") ? atoi(getenv("S2M2_ATTN_IMPL")) == 1 : 0;
+  if (!force_simt && attention_mma_supported(p)) return attention_mma_launch(p, (cudaStream_t)stream);
   return attention_simt_launch(p, (cudaStream_t)stream);
 }

@@ -1,0 +1,18 @@
+// Shared parameter block of the attention kernels (attention.cu: CUDA-core, attention_mma.cu: tensor-core).
+#pragma once
+#include "common.cuh"
+namespace s2m2 {
+struct AttnP {
+  const void* qkv;
+  void* out;
+  void* pesum;
+  const float *pe_x, *pe_y;
+  long long qkv_ld, out_ld;
+  int qh, oh, ph_half;
+  int S, N, heads, d, C, kv_shift, pe_h, pe_w;
+  float scale;
+};
+int attention_simt_launch(const AttnP& p, cudaStream_t s);
+int attention_mma_supported(const AttnP& p);
+int attention_mma_launch(const AttnP& p, cudaStream_t s);
+}  // namespace s2m2

@@ -1,0 +1,190 @@
+// Tensor-core flash attention for fp16 qkv (legacy mma.sync m16n8k16 path, fp32 accumulate / softmax).
+// One CTA = 64 queries of one (sequence, head), 4 warps x 16 rows; K/V tiles of 64 keys through shared memory;
+// online softmax in registers; P re-used as the A fragment of the PV product.
+// Used for every attention without the relative-PE term (attentions.py:50,86,91); the PE variant and head dims
+// that are not multiples of 16 / larger than 256 take the CUDA-core kernel in attention.cu.
+#include "attention.cuh"
+
+namespace s2m2 {
+
+constexpr int FA_BQ = 64, FA_BK = 64, FA_THREADS = 128;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *(uint32_t*)&h;
+}
+
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
+  constexpr int LDS = D + 8;               // padded row (halves): conflict-free ldmatrix
+  constexpr int KS = D / 16;               // k-steps of QK^T
+  constexpr int NG = FA_BK / 8;            // 8-key groups per tile
+  constexpr int OG = D / 8;                // 8-channel groups of the output
+  extern __shared__ __align__(16) __half sm[];
+  __half* Qs = sm;                         // [FA_BQ][LDS]
+  __half* Ks = Qs + FA_BQ * LDS;           // [FA_BK][LDS]
+  __half* Vs = Ks + FA_BK * LDS;           // [FA_BK][LDS]
+  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, s = blockIdx.z;
+  const int s_kv = (s + p.kv_shift) % p.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __half* base = (const __half*)p.qkv;
+  constexpr int CH = D / 8;                // 16-byte chunks per row
+
+  for (int e = tid; e < FA_BQ * CH; e += FA_THREADS) {
+    int r = e / CH, c = (e % CH) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < p.N) v = *(const uint4*)(base + ((long long)s * p.N + q0 + r) * p.qkv_ld + head * D + c);
+    *(uint4*)(Qs + r * LDS + c) = v;
+  }
+
+  float o[OG][4];
+#pragma unroll
+  for (int i = 0; i < OG; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;   // rows g and g+8 of this warp's 16-row slab
+  const float sl2 = p.scale * 1.4426950408889634f;       // softmax in base 2
+  const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+  const uint32_t k_addr = (uint32_t)__cvta_generic_to_shared(Ks + ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8);
+  const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+
+  for (int k0 = 0; k0 < p.N; k0 += FA_BK) {
+    __syncthreads();
+    for (int e = tid; e < FA_BK * CH; e += FA_THREADS) {
+      int r = e / CH, c = (e % CH) * 8;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+      if (k0 + r < p.N) {
+        const __half* src = base + ((long long)s_kv * p.N + k0 + r) * p.qkv_ld + head * D + c;
+        kv = *(const uint4*)(src + p.C);
+        vv = *(const uint4*)(src + 2 * p.C);
+      }
+      *(uint4*)(Ks + r * LDS + c) = kv;
+      *(uint4*)(Vs + r * LDS + c) = vv;
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (16 x 64 per warp)
+    float sc[NG][4];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(q_addr + ks * 32, a0, a1, a2, a3);
+#pragma unroll
+      for (int ng = 0; ng < NG; ng += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(k_addr + (ng * 8 * LDS + ks * 16) * 2, b0, b1, b2, b3);
+        mma16816(sc[ng], a0, a1, a2, a3, b0, b1);
+        mma16816(sc[ng + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    // ---- online softmax (rows g = lane/4 and g+8; columns 2t, 2t+1 of each 8-key group)
+    float mx0 = -1e30f, mx1 = -1e30f;
+#pragma unroll
+    for (int ng = 0; ng < NG; ++ng) {
+      int key = k0 + ng * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        bool ok = key + j < p.N;
+        sc[ng][j] = ok ? sc[ng][j] * sl2 : -1e30f;
+        sc[ng][2 + j] = ok ? sc[ng][2 + j] * sl2 : -1e30f;
+        mx0 = fmaxf(mx0, sc[ng][j]);
+        mx1 = fmaxf(mx1, sc[ng][2 + j]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int ng = 0; ng < NG; ++ng) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[ng][j] = exp2f(sc[ng][j] - mn0);
+        sc[ng][2 + j] = exp2f(sc[ng][2 + j] - mn1);
+        rs0 += sc[ng][j];
+        rs1 += sc[ng][2 + j];
+      }
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < OG; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < FA_BK / 16; ++kk) {
+      const uint32_t a0 = pack_h2(sc[2 * kk][0], sc[2 * kk][1]), a1 = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
+      const uint32_t a2 = pack_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]), a3 = pack_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int og = 0; og < OG; og += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(v_addr + (kk * 16 * LDS + og * 8) * 2, b0, b1, b2, b3);
+        mma16816(o[og], a0, a1, a2, a3, b0, b1);
+        mma16816(o[og + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  // ---- finalise: quad-reduce the row sums, normalise, store fp16
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __half* outp = (__half*)p.out;
+#pragma unroll
+  for (int og = 0; og < OG; ++og) {
+    const int c = head * D + og * 8 + (lane & 3) * 2;
+    if (r0 < p.N) *(__half2*)(outp + ((long long)s * p.N + r0) * p.out_ld + c) = __floats2half2_rn(o[og][0] * i0, o[og][1] * i0);
+    if (r1 < p.N) *(__half2*)(outp + ((long long)s * p.N + r1) * p.out_ld + c) = __floats2half2_rn(o[og][2] * i1, o[og][3] * i1);
+  }
+}
+
+template <int D>
+static int launch_fa(const AttnP& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)(FA_BQ + 2 * FA_BK) * (D + 8) * sizeof(__half);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  dim3 grid(cdiv(p.N, FA_BQ), p.heads, p.S);
+  attention_mma_kernel<D><<<grid, FA_THREADS, smem, s>>>(p);
+  S2M2_LAUNCH_OK("attention_mma");
+  return 0;
+}
+
+int attention_mma_supported(const AttnP& p) {
+  if (!p.qh || !p.oh || p.pesum) return 0;
+  if (p.qkv_ld % 8 || p.out_ld % 2 || !aligned(p.qkv, 16) || !aligned(p.out, 4)) return 0;
+  switch (p.d) {
+    case 16: case 32: case 64: case 96: case 128: case 192: case 256: return 1;
+    default: return 0;
+  }
+}
+
+int attention_mma_launch(const AttnP& p, cudaStream_t s) {
+  switch (p.d) {
+    case 16: return launch_fa<16>(p, s);
+    case 32: return launch_fa<32>(p, s);
+    case 64: return launch_fa<64>(p, s);
+    case 96: return launch_fa<96>(p, s);
+    case 128: return launch_fa<128>(p, s);
+    case 192: return launch_fa<192>(p, s);
+    case 256: return launch_fa<256>(p, s);
+  }
+  set_error("attention_mma: unsupported head dim %d", p.d);
+  return -1;
+}
+
+}  // namespace s2m2
