@@ -76,6 +76,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Threads for the CPU arm: the cgroup CPU quota if there is one (nproc can report far more cores than the
+    container may use, and eager PyTorch over-subscribes badly), capped at 32."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def run_reference(args, cfg_workload):
     """--impl reference: the reference's CPU algorithm (oracle port, fp32 eager torch ops) on the host cores."""
     from oracle import s2m2_oracle as O
@@ -84,7 +97,7 @@ def run_reference(args, cfg_workload):
     if rank != 0:
         return
     C, NTR = MODEL_TABLE[args.model]
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd = random_state_dict(C, NTR, 0)
     H, W = args.height, args.width
@@ -310,12 +323,19 @@ def main():
     line["vs_baseline_note"] = "value / 11.2 FPS (reference README TensorRT fp16 on ONE RTX 5090, L@1216x1024; BASELINE.md section 1)"
     if world == 1 and not args.no_cpu_baseline:
         from oracle import s2m2_oracle as O
-        cores = os.cpu_count() or 1
+        cores = host_threads()
         torch.set_num_threads(cores)
         sd = random_state_dict(C, NTR, 0)
-        sh, sw = (H, W) if H * W <= 640 * 480 else (H // 2 // 32 * 32, W // 2 // 32 * 32)
+        # bounded sample (~20 s): probe a small crop, then the largest crop (multiple of 32) that fits the budget
+        ph_, pw_ = min(H, 256), min(W, 320)
+        lp, rp = left_h[:1, :, :ph_, :pw_].contiguous(), right_h[:1, :, :ph_, :pw_].contiguous()
+        O.forward(sd, lp, rp, NTR, True, 3)
+        t0 = time.time()
+        O.forward(sd, lp, rp, NTR, True, 3)
+        tp = time.time() - t0
+        frac = min(1.0, 20.0 / max(tp * (H * W) / (ph_ * pw_), 1e-6))
+        sh, sw = max(ph_, int(H * frac ** 0.5) // 32 * 32), max(pw_, int(W * frac ** 0.5) // 32 * 32)
         l, r = left_h[:1, :, :sh, :sw].contiguous(), right_h[:1, :, :sh, :sw].contiguous()
-        O.forward(sd, l[..., :64, :64].contiguous(), r[..., :64, :64].contiguous(), NTR, True, 3)   # thread-pool warm-up
         t0 = time.time()
         O.forward(sd, l, r, NTR, True, 3)
         dt = time.time() - t0

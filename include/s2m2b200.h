@@ -86,7 +86,8 @@ int s2m2b200_pe_table(int32_t n, float* host_out);
 
 /* LayerNorm over C, eps 1e-5; gamma/beta NULL = no affine (attentions.py:117,...; submodules.py:165). */
 int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* gamma, const float* beta, void* stream);
-/* GroupNorm(groups, C), eps 1e-5, affine (submodules.py:80,90).  work: 2*N*groups doubles. */
+/* GroupNorm(groups, C), eps 1e-5, affine (submodules.py:80,90).  Deterministic (atomic-free) statistics.
+ * work: 2*N*groups*(1 + ceil(H*W/256)) doubles. */
 int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups, const float* gamma,
                        const float* beta, double* work, void* stream);
 /* AvgPool2d(2) (unet.py:25) and Upsample(x2, bilinear, align_corners=False) (unet.py:32). */

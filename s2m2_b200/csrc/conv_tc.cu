@@ -31,7 +31,7 @@ struct TcP {
   int flat;              // 1x1 conv: pixels are one flat dimension
   int Ho, Wo, Cout;      // output geometry (for flat: Wo = total pixels, Ho = 1)
   int tw, th, tiles_x, tiles_y;
-  int KW, ph, pw, taps;
+  int KW, ph, pw, taps, stride;
   int cpb1, cpb2;        // 64-channel chunks per tap from x and x2
   int act, shuffle, Cr;
 };
@@ -100,10 +100,15 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Tensor maps of one launch: act[0..3] = activation sources (stride 1: x, x2; stride 2: the four (row, column)
+// parity sub-sampled views of x, so that a strided convolution is a walk over plain strided views), w = weights.
+struct TcMaps {
+  CUtensorMap act[4];
+  CUtensorMap w;
+};
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmx,
-                                                                 const __grid_constant__ CUtensorMap tmx2,
-                                                                 const __grid_constant__ CUtensorMap tmw, const TcP p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcP p) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -161,9 +166,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int tap = kb / cpb, ch = kb - tap * cpb;
         const int ky = tap / p.KW, kx = tap - ky * p.KW;
         const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + s * B_BYTES);
-        if (ch < p.cpb1) tma_load_4d(&tmx, dstA, full0 + 8 * s, ch * TC_BK, x0 + kx - p.pw, y0 + ky - p.ph, img);
-        else tma_load_4d(&tmx2, dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + kx - p.pw, y0 + ky - p.ph, img);
-        tma_load_2d(&tmw, dstB, full0 + 8 * s, kb * TC_BK, n0);
+        const int dx = kx - p.pw, dy = ky - p.ph;
+        if (p.stride == 1) {
+          if (ch < p.cpb1) tma_load_4d(&maps.act[0], dstA, full0 + 8 * s, ch * TC_BK, x0 + dx, y0 + dy, img);
+          else tma_load_4d(&maps.act[1], dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + dx, y0 + dy, img);
+        } else {  // stride 2: input pixel (2y+dy, 2x+dx) lives in parity view (dy&1, dx&1) at (y + floor(dy/2), x + floor(dx/2))
+          tma_load_4d(&maps.act[(dy & 1) * 2 + (dx & 1)], dstA, full0 + 8 * s, ch * TC_BK, x0 + (dx >> 1), y0 + (dy >> 1), img);
+        }
+        tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -287,14 +297,21 @@ static bool tc_device_ok() {
 int conv_tc_supported(const S2m2Conv* a) {
   const S2m2Tensor &x = a->x, &x2 = a->x2, &y = a->y, &res = a->res;
   if (x.dtype != S2M2_F16 || a->w_dtype != S2M2_F16) return 0;
-  if (a->stride != 1 || (a->batch > 1)) return 0;
+  if (a->batch > 1) return 0;
+  if (a->stride == 2) {
+    if (a->KH != 3 || a->KW != 3 || a->pad_h != 1 || a->pad_w != 1 || x.H % 2 || x.W % 2 || x2.ptr || a->shuffle2x2) return 0;
+  } else if (a->stride != 1) {
+    return 0;
+  }
   if (x.C % TC_BK || x.ld % 8 || !aligned(x.ptr, 16)) return 0;
   if (x2.ptr && (x2.C % TC_BK || x2.ld % 8 || !aligned(x2.ptr, 16))) return 0;
   if (!aligned(a->w, 16)) return 0;
   if (a->Cout % 16 || a->Cout < 64) return 0;
   // same-size convolutions only (pad = k/2) or 1x1
-  const int Ho = x.H + 2 * a->pad_h - a->KH + 1, Wo = x.W + 2 * a->pad_w - a->KW + 1;
-  if (Ho != x.H || Wo != x.W) return 0;
+  if (a->stride == 1) {
+    const int Ho = x.H + 2 * a->pad_h - a->KH + 1, Wo = x.W + 2 * a->pad_w - a->KW + 1;
+    if (Ho != x.H || Wo != x.W) return 0;
+  }
   const int ye = y.dtype == S2M2_F16 ? 8 : 4;  // elements per 16 B
   if (y.ld % ye || !aligned(y.ptr, 16)) return 0;
   if (a->shuffle2x2) {
@@ -306,10 +323,17 @@ int conv_tc_supported(const S2m2Conv* a) {
   return tc_device_ok() ? 1 : 0;
 }
 
-static int encode_act(CUtensorMap* m, const S2m2Tensor& t, bool flat, int tw, int th) {
+static int encode_act(CUtensorMap* m, const S2m2Tensor& t, bool flat, int tw, int th, int parity = -1) {
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
-  if (flat) {
+  void* base = t.ptr;
+  if (parity >= 0) {  // every second row / column starting at (parity>>1, parity&1)
+    const int py = parity >> 1, px = parity & 1;
+    base = (char*)t.ptr + ((long long)py * t.W + px) * t.ld * 2;
+    dims[0] = t.C; dims[1] = t.W / 2; dims[2] = t.H / 2; dims[3] = t.N;
+    strides[0] = (cuuint64_t)t.ld * 2 * 2; strides[1] = (cuuint64_t)t.ld * 2 * t.W * 2; strides[2] = (cuuint64_t)t.ld * 2 * t.W * t.H;
+    box[0] = TC_BK; box[1] = tw; box[2] = th; box[3] = 1;
+  } else if (flat) {
     dims[0] = t.C; dims[1] = (cuuint64_t)t.N * t.H * t.W; dims[2] = 1; dims[3] = 1;
     strides[0] = (cuuint64_t)t.ld * 2; strides[1] = strides[0] * dims[1]; strides[2] = strides[1];
     box[0] = TC_BK; box[1] = TC_BM; box[2] = 1; box[3] = 1;
@@ -318,14 +342,14 @@ static int encode_act(CUtensorMap* m, const S2m2Tensor& t, bool flat, int tw, in
     strides[0] = (cuuint64_t)t.ld * 2; strides[1] = strides[0] * t.W; strides[2] = strides[1] * t.H;
     box[0] = TC_BK; box[1] = tw; box[2] = th; box[3] = 1;
   }
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
   return 0;
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtensorMap& mw, const TcP& p, dim3 grid, cudaStream_t s) {
+static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s) {
   constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
@@ -333,7 +357,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mx2, const CUtens
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(mx, mx2, mw, p);
+  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(maps, p);
   S2M2_LAUNCH_OK("conv_tc");
   return 0;
 }
@@ -345,7 +369,7 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   p.res_ld = res.ptr ? res.ld : 0; p.y_ld = y.ld;
   p.rh = res.ptr ? res.dtype == S2M2_F16 : 0; p.yh = y.dtype == S2M2_F16;
   p.flat = (a->KH == 1 && a->KW == 1) ? 1 : 0;
-  p.Cout = a->Cout; p.KW = a->KW; p.ph = a->pad_h; p.pw = a->pad_w; p.taps = a->KH * a->KW;
+  p.Cout = a->Cout; p.KW = a->KW; p.ph = a->pad_h; p.pw = a->pad_w; p.taps = a->KH * a->KW; p.stride = a->stride;
   p.cpb1 = x.C / TC_BK; p.cpb2 = x2.ptr ? x2.C / TC_BK : 0;
   p.act = a->act; p.shuffle = a->shuffle2x2; p.Cr = a->shuffle2x2 ? a->Cout / 4 : a->Cout;
   long long mtiles;
@@ -354,7 +378,7 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
     mtiles = p.tiles_x;
   } else {
     p.flat = 0;
-    p.Ho = x.H; p.Wo = x.W;
+    p.Ho = x.H / a->stride; p.Wo = x.W / a->stride;
     // patch shape: th*tw = 128, minimise padded-tile waste
     int best_tw = 16;
     long long best = -1;
@@ -367,27 +391,34 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
     p.tiles_x = cdiv(p.Wo, p.tw); p.tiles_y = cdiv(p.Ho, p.th);
     mtiles = (long long)p.tiles_x * p.tiles_y * x.N;
   }
-  CUtensorMap mx, mx2, mw;
-  if (int r = encode_act(&mx, x, p.flat, p.tw, p.th)) return r;
-  if (x2.ptr) {
-    if (int r = encode_act(&mx2, x2, p.flat, p.tw, p.th)) return r;
+  TcMaps maps;
+  if (a->stride == 2) {
+    for (int q = 0; q < 4; ++q)
+      if (int r = encode_act(&maps.act[q], x, false, p.tw, p.th, q)) return r;
   } else {
-    mx2 = mx;
+    if (int r = encode_act(&maps.act[0], x, p.flat, p.tw, p.th)) return r;
+    if (x2.ptr) {
+      if (int r = encode_act(&maps.act[1], x2, p.flat, p.tw, p.th)) return r;
+    } else {
+      maps.act[1] = maps.act[0];
+    }
+    maps.act[2] = maps.act[0];
+    maps.act[3] = maps.act[0];
   }
   const int BN = a->Cout >= 256 ? 256 : (a->Cout >= 128 ? 128 : 64);
   {
     const long long K = (long long)p.taps * (x.C + (x2.ptr ? x2.C : 0));
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Cout}, strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN}, estr[2] = {1, 1};
-    CUresult r = get_encode()(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
+    CUresult r = get_encode()(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
   dim3 grid((unsigned)mtiles, cdiv(a->Cout, BN));
-  if (BN == 256) return launch_tc<256, 4>(mx, mx2, mw, p, grid, s);
-  if (BN == 128) return launch_tc<128, 4>(mx, mx2, mw, p, grid, s);
-  return launch_tc<64, 4>(mx, mx2, mw, p, grid, s);
+  if (BN == 256) return launch_tc<256, 4>(maps, p, grid, s);
+  if (BN == 128) return launch_tc<128, 4>(maps, p, grid, s);
+  return launch_tc<64, 4>(maps, p, grid, s);
 }
 
 }  // namespace s2m2

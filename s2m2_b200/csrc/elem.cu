@@ -60,11 +60,11 @@ __global__ void layernorm_kernel(TV x, TV y, const float* __restrict__ gamma, co
 // ------------------------------------------------------------------------------------------------
 // GroupNorm: stats (sum, sumsq per (image, group) in double) then apply
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, double* __restrict__ stats) {
-  extern __shared__ float sh[];  // [groups][2]
+// Deterministic (atomic-free) reduction: per-block partial sums in a fixed order, then a fixed-order final sum.
+// part: [N][nblk][groups][2] doubles, stats: [N][groups][2] doubles.
+__global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, double* __restrict__ part) {
+  extern __shared__ float sh[];  // [nw][C][2]
   const int n = blockIdx.y, C = x.C, cpg = C / groups;
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -75,11 +75,26 @@ __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, dou
       s += v;
       q += v * v;
     }
-    atomicAdd(&sh[(c / cpg) * 2 + 0], s);
-    atomicAdd(&sh[(c / cpg) * 2 + 1], q);
+    sh[(wid * C + c) * 2 + 0] = s;
+    sh[(wid * C + c) * 2 + 1] = q;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)sh[i]);
+  if (threadIdx.x < 2 * groups) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    double acc = 0.0;
+    for (int w = 0; w < nw; ++w)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += (double)sh[(w * C + c) * 2 + k];
+    part[(((long long)n * gridDim.x + blockIdx.x) * groups + g) * 2 + k] = acc;
+  }
+}
+
+__global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int groups, int N, double* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g, k)
+  if (i >= N * groups * 2) return;
+  int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
+  double acc = 0.0;
+  for (int b = 0; b < nblk; ++b) acc += part[(((long long)n * nblk + b) * groups + g) * 2 + k];
+  stats[i] = acc;
 }
 
 __global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const double* __restrict__ stats,
@@ -276,14 +291,19 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "groupnorm: needs C,ld multiples of 4 and aligned bases");
   cudaStream_t s = (cudaStream_t)stream;
   const int HW = x->H * x->W;
-  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2 * x->N * groups, s);
-  S2M2_CHECK(e == cudaSuccess, "groupnorm: memset failed: %s", cudaGetErrorString(e));
-  const int ppb = 256;
-  dim3 grid(cdiv(HW, ppb), x->N);
-  gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(float), s>>>(tv(*x), HW, groups, ppb, work);
+  const int ppb = 256, nblk = cdiv(HW, ppb);
+  // work layout: stats [N][groups][2] doubles, then partials [N][nblk][groups][2] doubles
+  double* stats = work;
+  double* part = work + 2LL * x->N * groups;
+  dim3 grid(nblk, x->N);
+  const size_t smem = sizeof(float) * 2 * 8 * x->C;
+  S2M2_CHECK(smem <= 48 * 1024, "groupnorm: C=%d too large", x->C);
+  gn_stats_kernel<<<grid, 256, smem, s>>>(tv(*x), HW, groups, ppb, part);
   S2M2_LAUNCH_OK("gn_stats");
+  gn_final_kernel<<<cdiv(2LL * x->N * groups, 128), 128, 0, s>>>(part, nblk, groups, x->N, stats);
+  S2M2_LAUNCH_OK("gn_final");
   long long total4 = npix(*x) * (x->C / 4);
-  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, work, gamma, beta, total4);
+  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, stats, gamma, beta, total4);
   S2M2_LAUNCH_OK("gn_apply");
   return 0;
 }

@@ -109,8 +109,17 @@ class S2M2(nn.Module):
     def _adt(self):
         return torch.float16 if self.precision == "fp16" else torch.float32
 
-    def _mk(self, w4, b, stride=1, ph=None, pw=None, shuffle=False, name=""):
-        """w4: (Cout, Cin, KH, KW) fp32 conv weight -> ConvW (K order = tap-major, channel-minor)."""
+    def _mk(self, w4, b, stride=1, ph=None, pw=None, shuffle=False, name="", cin_to=None, cout_to=None):
+        """w4: (Cout, Cin, KH, KW) fp32 conv weight -> ConvW (K order = tap-major, channel-minor).
+
+        ``cin_to`` / ``cout_to`` zero-pad the channel counts (to multiples of 64 so the layer runs on the tcgen05
+        kernel); padded outputs are act(0 + 0) = 0 for GELU/ReLU and meet zero weights downstream."""
+        if cin_to is not None and cin_to > w4.shape[1]:
+            w4 = torch.cat([w4, w4.new_zeros(w4.shape[0], cin_to - w4.shape[1], *w4.shape[2:])], 1)
+        if cout_to is not None and cout_to > w4.shape[0]:
+            pad = cout_to - w4.shape[0]
+            w4 = torch.cat([w4, w4.new_zeros(pad, *w4.shape[1:])], 0)
+            b = torch.cat([b, b.new_zeros(pad)]) if b is not None else None
         cout, cin, kh, kw = w4.shape
         ph = kh // 2 if ph is None else ph
         pw = kw // 2 if pw is None else pw
@@ -121,6 +130,10 @@ class S2M2(nn.Module):
     def _conv(self, name, stride=1, **kw):
         b = self._w(name + ".bias") if self._has(name + ".bias") else None
         return self._mk(self._w(name + ".weight"), b, stride=stride, name=name, **kw)
+
+    def _convT1(self, name, **kw):
+        w = self._w(name + ".weight")
+        return self._mk(w.permute(1, 0, 2, 3).contiguous(), self._w(name + ".bias"), name=name, **kw)
 
     def _lin(self, name):
         w = self._w(name + ".weight")
@@ -149,10 +162,6 @@ class S2M2(nn.Module):
         """ConvTranspose2d(k=3,p=1,s=1) == 3x3 conv with flipped, in/out-transposed weights."""
         w = self._w(name + ".weight")
         return self._mk(w.flip(2, 3).permute(1, 0, 2, 3).contiguous(), self._w(name + ".bias"), name=name)
-
-    def _convT1(self, name):
-        w = self._w(name + ".weight")
-        return self._mk(w.permute(1, 0, 2, 3).contiguous(), self._w(name + ".bias"), name=name)
 
     def _pack_attn(self, p, heads, pe=False):
         q, k, v = self._lin(p + ".q"), self._lin(p + ".k"), self._lin(p + ".v")
@@ -224,10 +233,11 @@ class S2M2(nn.Module):
         P["di_w"] = self._w("disp_init.layer_norm.weight").float().contiguous()
         P["di_b"] = self._w("disp_init.layer_norm.bias").float().contiguous()
         # global refiner: input channel order in the reference is [disp, conf_logit, ctx(C)] (refinenet.py:68);
-        # we feed [ctx(C), disp, conf_logit, 6 zero pad] so the channel count stays a multiple of 8.
+        # we run the conv over two sources [ctx(C) | aux(64): disp, conf_logit, 62 zeros]: ctx is read in place
+        # (no concat copy) and both sources are multiples of 64 channels (tcgen05 path).
         g = "global_refiner"
         w = self._w(f"{g}.init_feat.0.weight")                        # (C, 2+C, 3, 3)
-        wpad = torch.zeros(w.shape[0], C + 8, 3, 3, device=w.device)
+        wpad = torch.zeros(w.shape[0], C + 64, 3, 3, device=w.device)
         wpad[:, :C] = w[:, 2:]
         wpad[:, C:C + 2] = w[:, :2]
         out_w = self._w(f"{g}.out_feat.0.weight") * 1e2               # fold the *1e2 (refinenet.py:71)
@@ -238,9 +248,9 @@ class S2M2(nn.Module):
         P["ffl"] = self._pack_fusion("feat_fusion_layer")
         P["ctx0"], P["ctx2"] = self._conv("ctx_feat.0"), self._conv("ctx_feat.2")
         r = "refiner"
-        P["lr"] = {"df0": self._conv(f"{r}.disp_feat.0"), "df2": self._conv(f"{r}.disp_feat.2"),
-                   "cf10": self._conv(f"{r}.corr_feat1.0"), "cf12": self._conv(f"{r}.corr_feat1.2"),
-                   "cf20": self._conv(f"{r}.corr_feat2.0"), "cf22": self._conv(f"{r}.corr_feat2.2"),
+        P["lr"] = {"df0": self._conv(f"{r}.disp_feat.0", cout_to=128), "df2": self._conv(f"{r}.disp_feat.2", cin_to=128),
+                   "cf10": self._conv(f"{r}.corr_feat1.0", cout_to=128), "cf12": self._conv(f"{r}.corr_feat1.2", cin_to=128),
+                   "cf20": self._conv(f"{r}.corr_feat2.0", cout_to=128), "cf22": self._conv(f"{r}.corr_feat2.2", cin_to=128),
                    "co0": self._conv(f"{r}.conf_occ_feat.0"), "co2": self._conv(f"{r}.conf_occ_feat.2"),
                    "cat0": self._conv(f"{r}.disp_corr_ctx_cat.0"), "cat2": self._conv(f"{r}.disp_corr_ctx_cat.2"),
                    "unet": self._pack_unet(f"{r}.refine_unet", 1, False),
@@ -256,8 +266,8 @@ class S2M2(nn.Module):
                    "c0": self._conv(f"{u}.conv_concat.0"), "c2": self._convT2(f"{u}.conv_concat.2")}
         u = "upsample_mask_1x"
         P["u1"] = {"disp": self._convT3(f"{u}.conv_disp.0"), "rgb": self._convT3(f"{u}.conv_rgb.0"),
-                   "ctx": self._convT2(f"{u}.conv_ctx"), "c0": self._conv(f"{u}.conv_concat.0"),
-                   "c2": self._convT1(f"{u}.conv_concat.2")}
+                   "ctx": self._convT2(f"{u}.conv_ctx"), "c0": self._conv(f"{u}.conv_concat.0", cin_to=64, cout_to=64),
+                   "c2": self._convT1(f"{u}.conv_concat.2", cin_to=64)}
         return P
 
     def _ensure_packed(self, device):
@@ -469,10 +479,9 @@ class S2M2(nn.Module):
 
         # -- global refiner (refinenet.py:59-73)
         gr = P["gr"]
-        gin = ops.zeros((B, h4, w4, C + 8), adt, dev)
-        ops.copy_channels(ftr0, gin[..., :C])
-        ops.global_refiner_prep(disp, conf, gin[..., C:C + 2])
-        feat = self._c(self._c(gin, gr["i0"], ACT_GELU), gr["i2"])
+        gaux = ops.zeros((B, h4, w4, 64), adt, dev)
+        ops.global_refiner_prep(disp, conf, gaux[..., 0:2])
+        feat = self._c(self._c(ftr0, gr["i0"], ACT_GELU, x2=gaux), gr["i2"])
         rf = self._unet(feat, gr["unet"])[0]
         upd = self._c(rf, gr["out"], out_dtype=f32)                    # already scaled by 1e2
         ops.global_refiner_merge(disp, conf, upd, self.use_positivity)  # in place on disp
@@ -535,7 +544,7 @@ class S2M2(nn.Module):
 
         # -- edge-guided 1x filter (submodules.py:137-145, s2m2.py:116-133,190-193)
         u1 = P["u1"]
-        m1in = ops.empty((B, H, W, 48), adt, dev)
+        m1in = ops.zeros((B, H, W, 64), adt, dev)                       # disp 16 | rgb 16 | ctx 16 | 16 zero pad
         self._c(up[..., 0:1], u1["disp"], ACT_RELU, out=m1in[..., 0:16])
         self._c(img[:B], u1["rgb"], ACT_RELU, out=m1in[..., 16:32])
         self._c(f2_0, u1["ctx"], out=m1in[..., 32:48])

@@ -179,9 +179,10 @@ class CudaOps:
         self._chk(self.lib.s2m2b200_layernorm(C.byref(xt), C.byref(yt), g, b, self._stream()), "layernorm")
 
     def groupnorm(self, x, groups, gamma, beta, out):
-        key = (x.shape[0], groups, str(x.device))
+        nblk = (x.shape[1] * x.shape[2] + 255) // 256
+        key = (x.shape[0], groups, nblk, str(x.device))
         if key not in self._gn_work:
-            self._gn_work[key] = torch.zeros(2 * x.shape[0] * groups, dtype=torch.float64, device=x.device)
+            self._gn_work[key] = torch.zeros(2 * x.shape[0] * groups * (1 + nblk), dtype=torch.float64, device=x.device)
         work = self._gn_work[key]
         xt, yt = tview(x), tview(out)
         self._chk(self.lib.s2m2b200_groupnorm(C.byref(xt), C.byref(yt), groups, C.c_void_p(gamma.data_ptr()),

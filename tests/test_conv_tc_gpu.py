@@ -9,6 +9,8 @@ from torch_ops import TorchOps
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 CASES = [
     # N, H, W, C1, C2, Cout, kh, kw, act, res, shuffle, out_f32, in_ld_extra
@@ -25,6 +27,8 @@ CASES = [
     (1, 16, 24, 128, 0, 96, 3, 3, ACT_NONE, False, False, True, 0),       # fp32 output, Cout=96
     (1, 8, 152, 512, 0, 512, 1, 1, ACT_GELU, True, False, False, 0),      # K=512, N=512
     (2, 32, 38, 512, 0, 512, 3, 3, ACT_NONE, False, False, False, 0),     # 1/32-res style 3x3, K=4608
+    (2, 24, 36, 128, 0, 128, 3, 3, ACT_NONE, False, False, False, 0, 2),  # 3x3 stride 2 (conv2_down) via parity views
+    (1, 64, 76, 256, 0, 256, 3, 3, ACT_GELU, False, False, False, 0, 2),  # 3x3 stride 2, N=256
 ]
 
 
@@ -32,17 +36,18 @@ CASES = [
 def test_conv_tc(case):
     from s2m2_b200.ops import CudaOps
     cu, th = CudaOps(conv_impl=2), TorchOps()
-    N, H, W, C1, C2, Cout, kh, kw, act, use_res, shuffle, out_f32, ldx = case
+    N, H, W, C1, C2, Cout, kh, kw, act, use_res, shuffle, out_f32, ldx = case[:13]
+    stride = case[13] if len(case) > 13 else 1
     g = torch.Generator().manual_seed(abs(hash(case)) % 1000)
     Cin = C1 + C2
     K = kh * kw * Cin
     w = (torch.randn((Cout, K), generator=g) / math.sqrt(K)).to(DEV).half()
     b = (torch.randn((Cout,), generator=g) * 0.5).to(DEV)
-    cw = ConvW(w, b, kh, kw, 1, kh // 2, kw // 2, Cin, Cout, shuffle, "tc")
+    cw = ConvW(w, b, kh, kw, stride, kh // 2, kw // 2, Cin, Cout, shuffle, "tc")
     xb = torch.randn((N, H, W, C1 + ldx), generator=g).to(DEV).half()
     x = xb[..., :C1] if ldx else xb
     x2 = torch.randn((N, H, W, C2), generator=g).to(DEV).half() if C2 else None
-    oshape = (N, 2 * H, 2 * W, Cout // 4) if shuffle else (N, H, W, Cout)
+    oshape = (N, 2 * H, 2 * W, Cout // 4) if shuffle else (N, H // stride, W // stride, Cout)
     odt = torch.float32 if out_f32 else torch.float16
     res = torch.randn(oshape, generator=g).to(DEV).half() if use_res else None
     a = torch.full(oshape, 7.0, dtype=odt, device=DEV)

@@ -12,6 +12,9 @@ from torch_ops import TorchOps
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+# the torch restatement is the fp32 checker: no TF32 in its convolutions / matmuls
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="module")

@@ -75,18 +75,26 @@ def test_fp32_argmax_and_masks_bit_exact_vs_oracle():
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES[:2] + GOLDEN_CASES[3:])
-def test_fp16_path_close_to_reference_golden(name):
+def test_fp16_path_no_worse_than_reference_autocast(name):
+    """fp16 mode vs the fp32 golden, judged against the reference algorithm's OWN fp16 behaviour: the oracle under
+    torch.autocast(fp16) (how run_stereo_matching runs the reference, model_utils.py:76) on the same inputs.
+    With random-init weights the matching is nearly flat, so fp16 flips some arg-maxes in either implementation;
+    the bound is 2x the autocast EPE (floor 5e-3 px, the BASELINE.md section-3 figure)."""
     cfg, g = load_golden(name)
     sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
     m = _model(cfg["C"], cfg["NTR"], sd, cfg["pos"], cfg["it"], "fp16")
     left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
     d, o, c = (t.cpu() for t in m(left.to(DEV), right.to(DEV)))
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.float16):
+        ac = O.forward(sdg, left.to(DEV), right.to(DEV), cfg["NTR"], cfg["pos"], cfg["it"])
     epe = (d - g["disp"]).abs().mean().item()
-    print(f"{name} fp16: EPE {epe:.3e} max {(d - g['disp']).abs().max().item():.3e}")
-    scale = max(1.0, g["disp"].abs().max().item() / 4)
+    epe_ac = (ac[0].float().cpu() - g["disp"]).abs().mean().item()
+    print(f"{name} fp16: EPE {epe:.3e} max {(d - g['disp']).abs().max().item():.3e} | reference-autocast EPE {epe_ac:.3e}")
     assert torch.isfinite(d).all() and torch.isfinite(o).all() and torch.isfinite(c).all()
-    assert epe < 5e-2 * scale                      # reference autocast-fp16 itself: 7e-3
-    assert (o - g["occ"]).abs().mean() < 2e-2 and (c - g["conf"]).abs().mean() < 2e-2
+    assert epe < max(2 * epe_ac, 5e-3)
+    assert (o - g["occ"]).abs().mean() < max(2 * (ac[1].float().cpu() - g["occ"]).abs().mean().item(), 5e-3)
+    assert (c - g["conf"]).abs().mean() < max(2 * (ac[2].float().cpu() - g["conf"]).abs().mean().item(), 5e-3)
 
 
 def test_s_640x480_vs_oracle_on_gpu():
