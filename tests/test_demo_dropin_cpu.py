@@ -38,6 +38,12 @@ def test_unmodified_demo_runs_with_dropin_module(tmp_path, monkeypatch, capsys):
             return self._last
 
     monkeypatch.setattr(model_mod, "S2M2", CpuBacked)
+    # the launcher rebinds s2m2.core.model.s2m2.S2M2 for the process: undo it after this test
+    sys.path.insert(0, os.path.join(REF, "src"))
+    import s2m2.core.model.s2m2 as ref_mod
+    monkeypatch.setattr(ref_mod, "S2M2", ref_mod.S2M2)
+    for k in [k for k in sys.modules if k.startswith("s2m2.core.utils")]:
+        monkeypatch.delitem(sys.modules, k, raising=False)
 
     class FakeEvent:
         def __init__(self, enable_timing=False):
@@ -58,3 +64,5 @@ def test_unmodified_demo_runs_with_dropin_module(tmp_path, monkeypatch, capsys):
     assert "cropped image size: img_height(1088), img_width(800)" in out
     assert "FPS:" in out
     assert calls["n"] == 6
+    for k in [k for k in sys.modules if k.startswith("s2m2.core.utils")]:
+        monkeypatch.delitem(sys.modules, k, raising=False)
