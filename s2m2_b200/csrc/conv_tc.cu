@@ -14,6 +14,7 @@
 // Reference ops replaced: the big nn.Conv2d / nn.Linear / ConvTranspose2d(k=2) layers (include/s2m2b200.h).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -264,6 +265,237 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
 }
 
+
+// =====================================================================================================
+// v2: persistent kernel.  One CTA per SM loops over output tiles (n-tile major so concurrently running CTAs
+// share the weight tile in L2); two TMEM accumulators so the epilogue of tile i overlaps the mainloop of tile
+// i+1; 16 epilogue warps (4 per TMEM lane quarter, each a quarter of the columns — the GELU epilogue, not the
+// MMA, is the critical path of the K=256 GEMMs); the smem ring keeps streaming across tile boundaries.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue.
+// =====================================================================================================
+constexpr int TC2_EPI_GROUPS = 4;                       // epilogue warps per TMEM lane quarter
+constexpr int TC2_THREADS = 64 + 128 * TC2_EPI_GROUPS;   // 576
+
+// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26) — far below fp16 output rounding; the exact erff costs
+// about twice as many instructions and the GELU epilogue is the critical path of the small-K GEMMs.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float r = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float act_fast(float x, int act) {
+  switch (act) {
+    case S2M2_ACT_GELU: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));
+    case S2M2_ACT_RELU: return fmaxf(x, 0.0f);
+    case S2M2_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
+    case S2M2_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcP p,
+                                                                            int m_tiles, int n_tiles) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + STAGES * B_BYTES);  // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const int cpb = p.cpb1 + p.cpb2;
+  const int nkb = p.taps * cpb;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4 * TC2_EPI_GROUPS);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> coordinates (n-tile major: tile = nt * m_tiles + mt)
+  auto tile_coords = [&](int tile, int& n0, int& img, int& x0, int& y0) {
+    const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+    n0 = nt * BN;
+    img = 0; y0 = 0;
+    if (p.flat) {
+      x0 = mt * TC_BM;
+    } else {
+      const int txi = mt % p.tiles_x;
+      const int t = mt / p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      img = t / p.tiles_y;
+      x0 = txi * p.tw;
+      y0 = tyi * p.th;
+    }
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;  // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, img, x0, y0;
+        tile_coords(tile, n0, img, x0, y0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+          const int tap = kb / cpb, ch = kb - tap * cpb;
+          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + s * B_BYTES);
+          const int dx = kx - p.pw, dy = ky - p.ph;
+          if (p.stride == 1) {
+            if (ch < p.cpb1) tma_load_4d(&maps.act[0], dstA, full0 + 8 * s, ch * TC_BK, x0 + dx, y0 + dy, img);
+            else tma_load_4d(&maps.act[1], dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + dx, y0 + dy, img);
+          } else {
+            tma_load_4d(&maps.act[(dy & 1) * 2 + (dx & 1)], dstA, full0 + 8 * s, ch * TC_BK, x0 + (dx >> 1), y0 + (dy >> 1), img);
+          }
+          tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t it = 0, lt = 0;  // k-block counter, local tile counter
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);          // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ad = make_sdesc(smem_u32(sA + s * A_BYTES)), bd = make_sdesc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    // ================= epilogue: warp%4 = TMEM lane quarter, (warp-2)/4 = column group =================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CG = BN / TC2_EPI_GROUPS;   // columns per group
+    const int r = q * 32 + lane;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      int n0, img, x0, y0;
+      tile_coords(tile, n0, img, x0, y0);
+      const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+      bool valid;
+      long long opix;
+      int py = 0, px = 0;
+      if (p.flat) {
+        valid = x0 + r < p.Wo;
+        opix = x0 + r;
+      } else {
+        py = y0 + r / p.tw;
+        px = x0 + r % p.tw;
+        valid = py < p.Ho && px < p.Wo;
+        opix = ((long long)img * p.Ho + py) * p.Wo + px;
+      }
+      mbar_wait(tfull0 + 8 * acc, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * CG; c0 < (half + 1) * CG; c0 += 16) {
+        const int n = n0 + c0;
+        if (n >= p.Cout) break;
+        uint32_t rr[16];
+        tmem_ld16(trow + c0, rr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!valid) continue;
+        float v[16];
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bb = __ldg((const float4*)(p.bias + n + i));
+            v[i] = __uint_as_float(rr[i]) + bb.x; v[i + 1] = __uint_as_float(rr[i + 1]) + bb.y;
+            v[i + 2] = __uint_as_float(rr[i + 2]) + bb.z; v[i + 3] = __uint_as_float(rr[i + 3]) + bb.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+        }
+        if (p.act != S2M2_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = act_fast(v[i], p.act);
+        }
+        long long off;
+        if (p.shuffle) {
+          const int qd = n / p.Cr, co = n - qd * p.Cr;
+          const long long pix = ((long long)img * 2 * p.Ho + 2 * py + (qd >> 1)) * (2 * p.Wo) + 2 * px + (qd & 1);
+          off = pix * p.y_ld + co;
+        } else {
+          off = opix * p.y_ld + n;
+          if (p.res) {
+            const long long ro = opix * p.res_ld + n;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 t = ld4(p.res, ro + i, p.rh);
+              v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+            }
+          }
+        }
+        if (p.yh) {
+          __half2 h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+          uint4* dst = (uint4*)((__half*)p.y + off);
+          dst[0] = *(uint4*)&h[0];
+          dst[1] = *(uint4*)&h[4];
+        } else {
+          float4* dst = (float4*)((float*)p.y + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      // all of this warp's TMEM reads have completed (wait::ld above): hand the accumulator back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -302,7 +534,7 @@ int conv_tc_supported(const S2m2Conv* a) {
   }
   if (x.C % TC_BK || x.ld % 8 || !aligned(x.ptr, 16)) return 0;
   if (x2.ptr && (x2.C % TC_BK || x2.ld % 8 || !aligned(x2.ptr, 16))) return 0;
-  if (!aligned(a->w, 16)) return 0;
+  if (!aligned(a->w, 16) || (a->bias && !aligned(a->bias, 16))) return 0;
   if (a->Cout % 16 || a->Cout < 64) return 0;
   // same-size convolutions only (pad = k/2) or 1x1
   if (a->stride == 1) {
@@ -359,6 +591,26 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
   return 0;
 }
 
+template <int BN, int STAGES>
+static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles, cudaStream_t s) {
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const long long tiles = (long long)m_tiles * n_tiles;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  conv_tc_persistent_kernel<BN, STAGES><<<grid, TC2_THREADS, smem, s>>>(maps, p, m_tiles, n_tiles);
+  S2M2_LAUNCH_OK("conv_tc_persistent");
+  return 0;
+}
+
 int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   const S2m2Tensor &x = a->x, &x2 = a->x2, &y = a->y, &res = a->res;
   TcP p{};
@@ -411,6 +663,13 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+  static const int use_v1 = getenv("S2M2_TC_V1") ? atoi(getenv("S2M2_TC_V1")) : 0;
+  if (!use_v1) {
+    const int nt = cdiv(a->Cout, BN);
+    if (BN == 256) return launch_tc2<256, 4>(maps, p, (int)mtiles, nt, s);
+    if (BN == 128) return launch_tc2<128, 6>(maps, p, (int)mtiles, nt, s);
+    return launch_tc2<64, 8>(maps, p, (int)mtiles, nt, s);
   }
   dim3 grid((unsigned)mtiles, cdiv(a->Cout, BN));
   if (BN == 256) return launch_tc<256, 4>(maps, p, grid, s);

@@ -141,6 +141,33 @@ def test_s_640x480_vs_oracle_on_gpu():
     assert epe16 < 5e-2
 
 
+def test_l_1216x1024_headline_config_vs_oracle_on_gpu():
+    """BASELINE config 3 (L, 1216x1024, refine_iter=3), the headline: both precisions vs the fp32 oracle (TF32 off)."""
+    C, NTR = 256, 3
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, 1024, 1216, 1)
+    ot = {}
+    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3, ot)]
+    am_ref = ot["disp_init.argmax"].cpu()
+    del ot
+    torch.cuda.empty_cache()
+    for prec, tol in (("fp32", 1e-3), ("fp16", 1e-3)):
+        m = _model(C, NTR, sd, precision=prec)
+        m.taps = {}
+        out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+        flips = int((m.taps["disp_init.argmax"].cpu() != am_ref).sum())
+        m.taps = None
+        err = (out[0] - ref[0]).abs()
+        print(f"L 1216x1024 {prec}: EPE {err.mean().item():.3e} max {err.max().item():.3e} argmax flips {flips}/{am_ref.numel()} "
+              f"occ {(out[1] - ref[1]).abs().mean().item():.2e} conf {(out[2] - ref[2]).abs().mean().item():.2e}")
+        assert torch.isfinite(out[0]).all()
+        assert err.mean().item() < tol           # north_star: EPE < 1e-3 px vs the fp32 reference
+        if prec == "fp32":
+            assert flips == 0
+        del m
+        torch.cuda.empty_cache()
+
+
 def test_batch_independence_and_determinism():
     """Pairs are independent units: a batch of two identical pairs gives two identical results,
     equal to the single-pair result, and repeated calls are bit-identical."""
