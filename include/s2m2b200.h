@@ -114,15 +114,16 @@ int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h,
 
 /* GlobalRefiner glue (refinenet.py:63-66,72): out[...,0] = disp/100*mask, out[...,1] = logit(mask*conf, .1). */
 int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t npix, const S2m2Tensor* out, void* stream);
-/* disp = mask*disp + (1-mask)*upd (upd pre-scaled by 100), optional clamp >= 0 (s2m2.py:160-161). */
-int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t npix,
+/* disp = mask*disp + (1-mask)*upd[i*upd_ld] (upd pre-scaled by 100), optional clamp >= 0 (s2m2.py:160-161). */
+int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t upd_ld, int64_t npix,
                                   int32_t use_positivity, void* stream);
 /* LocalRefiner glue (refinenet.py:134-135,140): small (npix,4) = disp/100 | logit(conf,.01) | logit(occ,.01) | 0. */
 int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const float* occ, int64_t npix,
                                 float* small, void* stream);
-/* refinenet.py:147-154 + s2m2.py:177-180: disp += dd; conf/occ = sigmoid(delta + logit); clamp; occ *= (x - disp >= 0). */
-int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* dd,
-                                  const float* co, int32_t B, int32_t h, int32_t w, int32_t use_positivity, void* stream);
+/* refinenet.py:147-154 + s2m2.py:177-180: upd (npix, upd_ld >= 3) fp32 = [delta disp | delta conf logit | delta occ logit | ...]:
+ * disp += upd0; conf/occ = sigmoid(upd1/2 + logit); clamp; occ *= (x - disp >= 0). */
+int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* upd,
+                                  int64_t upd_ld, int32_t B, int32_t h, int32_t w, int32_t use_positivity, void* stream);
 
 /* RAFT convex 4x upsampling of disp*4 | occ | conf with one set of 9 logits (s2m2.py:101-114,184-187):
  * logits (B,4h,4w,9) fp32 -> up (B,4h,4w,4) fp32 (4th channel 0). */

@@ -25,7 +25,13 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *(uint32_t*)&h;
 }
 
-template <int D>
+// PE = true: 2-D attention with the contextual relative-PE term (attentions.py:42-48).  Key tiles are then whole
+// image rows of the (pe_h x pe_w) token grid (pe_w <= 64), so that
+//     pesum[q, 0:16]  = .5 * sum_xj  Mx[q, xj] * pe_x[xq - xj + w - 1],   Mx[q, xj] = sum_yj P[q, (yj, xj)]
+//     pesum[q, 16:32] = .5 * sum_yj  My[q, yj] * pe_y[yq - yj + h - 1],   My[q, yj] = sum_xj P[q, (yj, xj)]
+// only needs the two marginals of P: Mx accumulates in registers (a thread always owns the same key columns),
+// My is one row-sum per tile.  The (N, N, 32) tensor of utils.py:32-60 never exists.
+template <int D, bool PE>
 __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   constexpr int LDS = D + 8;               // padded row (halves): conflict-free ldmatrix
   constexpr int KS = D / 16;               // k-steps of QK^T
@@ -35,6 +41,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   __half* Qs = sm;                         // [FA_BQ][LDS]
   __half* Ks = Qs + FA_BQ * LDS;           // [FA_BK][LDS]
   __half* Vs = Ks + FA_BK * LDS;           // [FA_BK][LDS]
+  float* My_raw = (float*)(Vs + FA_BK * LDS);   // PE: [FA_BQ][pe_h] row sums at the running max of that time
+  float* M_at = My_raw + FA_BQ * (PE ? p.pe_h : 0);   // PE: [FA_BQ][pe_h] that running max
+  float* Mxs = M_at + FA_BQ * (PE ? p.pe_h : 0);      // PE: [FA_BQ][FA_BK] x-marginal (written at the end)
   const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, s = blockIdx.z;
   const int s_kv = (s + p.kv_shift) % p.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -57,12 +66,19 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   const uint32_t k_addr = (uint32_t)__cvta_generic_to_shared(Ks + ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8);
   const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
 
-  for (int k0 = 0; k0 < p.N; k0 += FA_BK) {
+  float mxr[PE ? NG : 1][4];               // PE: x-marginal of P for rows g, g+8 at key columns 8*ng + 2t, +1
+#pragma unroll
+  for (int i = 0; i < (PE ? NG : 1); ++i) mxr[i][0] = mxr[i][1] = mxr[i][2] = mxr[i][3] = 0.f;
+  const int kstep = PE ? p.pe_w : FA_BK;    // keys per tile
+  int tile_i = 0;
+
+  for (int k0 = 0; k0 < p.N; k0 += kstep, ++tile_i) {
+    const int kend = PE ? k0 + kstep : p.N;  // first key NOT in this tile
     __syncthreads();
     for (int e = tid; e < FA_BK * CH; e += FA_THREADS) {
       int r = e / CH, c = (e % CH) * 8;
       uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-      if (k0 + r < p.N) {
+      if (k0 + r < kend) {
         const __half* src = base + ((long long)s_kv * p.N + k0 + r) * p.qkv_ld + head * D + c;
         kv = *(const uint4*)(src + p.C);
         vv = *(const uint4*)(src + 2 * p.C);
@@ -95,7 +111,7 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
       int key = k0 + ng * 8 + (lane & 3) * 2;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        bool ok = key + j < p.N;
+        bool ok = key + j < kend;
         sc[ng][j] = ok ? sc[ng][j] * sl2 : -1e30f;
         sc[ng][2 + j] = ok ? sc[ng][2 + j] * sl2 : -1e30f;
         mx0 = fmaxf(mx0, sc[ng][j]);
@@ -120,6 +136,21 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
     }
     l0 = l0 * c0 + rs0;
     l1 = l1 * c1 + rs1;
+    if constexpr (PE) {
+#pragma unroll
+      for (int ng = 0; ng < NG; ++ng) {
+        mxr[ng][0] = mxr[ng][0] * c0 + sc[ng][0]; mxr[ng][1] = mxr[ng][1] * c0 + sc[ng][1];
+        mxr[ng][2] = mxr[ng][2] * c1 + sc[ng][2]; mxr[ng][3] = mxr[ng][3] * c1 + sc[ng][3];
+      }
+      float t0 = rs0, t1 = rs1;   // this tile's row sums: y-marginal for image row tile_i
+      t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+      if ((lane & 3) == 0) {
+        const int rr0 = warp * 16 + (lane >> 2);
+        My_raw[rr0 * p.pe_h + tile_i] = t0;       M_at[rr0 * p.pe_h + tile_i] = mn0;
+        My_raw[(rr0 + 8) * p.pe_h + tile_i] = t1; M_at[(rr0 + 8) * p.pe_h + tile_i] = mn1;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < OG; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
     // ---- O += P V
@@ -141,6 +172,48 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
   const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  if constexpr (PE) {
+    // publish the normalised marginals, then every thread produces 16 of the 64 x 32 PE sums of this query tile
+    const int lr0 = warp * 16 + (lane >> 2), lr1 = lr0 + 8;
+#pragma unroll
+    for (int ng = 0; ng < NG; ++ng) {
+      const int c = ng * 8 + (lane & 3) * 2;
+      Mxs[lr0 * FA_BK + c] = mxr[ng][0] * i0; Mxs[lr0 * FA_BK + c + 1] = mxr[ng][1] * i0;
+      Mxs[lr1 * FA_BK + c] = mxr[ng][2] * i1; Mxs[lr1 * FA_BK + c + 1] = mxr[ng][3] * i1;
+    }
+    if ((lane & 3) == 0) {
+      for (int y = 0; y < p.pe_h; ++y) {
+        My_raw[lr0 * p.pe_h + y] *= exp2f(M_at[lr0 * p.pe_h + y] - m0) * i0;
+        My_raw[lr1 * p.pe_h + y] *= exp2f(M_at[lr1 * p.pe_h + y] - m1) * i1;
+      }
+    }
+    __syncthreads();
+    const int ql = tid & 63, part = tid >> 6;      // part 0: x half (channels 0..15), part 1: y half (16..31)
+    const int t = q0 + ql;
+    if (t < p.N) {
+      const int xq = t % p.pe_w, yq = t / p.pe_w;
+      float acc[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      const int n = part == 0 ? p.pe_w : p.pe_h;
+      const float* tab = part == 0 ? p.pe_x : p.pe_y;
+      const float* mg = part == 0 ? Mxs + ql * FA_BK : My_raw + ql * p.pe_h;
+      const int qc = part == 0 ? xq : yq;
+      for (int j = 0; j < n; ++j) {
+        const float w = 0.5f * mg[j];
+        const float4* row = (const float4*)(tab + (qc - j + n - 1) * 16);
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 tv = __ldg(row + e4);
+          acc[4 * e4] = fmaf(w, tv.x, acc[4 * e4]); acc[4 * e4 + 1] = fmaf(w, tv.y, acc[4 * e4 + 1]);
+          acc[4 * e4 + 2] = fmaf(w, tv.z, acc[4 * e4 + 2]); acc[4 * e4 + 3] = fmaf(w, tv.w, acc[4 * e4 + 3]);
+        }
+      }
+      __half* ps = (__half*)p.pesum + (((long long)s * p.N + t) * p.heads + head) * 32 + part * 16;
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) *(__half2*)(ps + e) = __floats2half2_rn(acc[e], acc[e + 1]);
+    }
+  }
   __half* outp = (__half*)p.out;
 #pragma unroll
   for (int og = 0; og < OG; ++og) {
@@ -150,22 +223,28 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   }
 }
 
-template <int D>
+template <int D, bool PE>
 static int launch_fa(const AttnP& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)(FA_BQ + 2 * FA_BK) * (D + 8) * sizeof(__half);
+  const size_t smem = (size_t)(FA_BQ + 2 * FA_BK) * (D + 8) * sizeof(__half) +
+                      (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
+  S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attention_mma_kernel<D, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
   dim3 grid(cdiv(p.N, FA_BQ), p.heads, p.S);
-  attention_mma_kernel<D><<<grid, FA_THREADS, smem, s>>>(p);
+  attention_mma_kernel<D, PE><<<grid, FA_THREADS, smem, s>>>(p);
   S2M2_LAUNCH_OK("attention_mma");
   return 0;
 }
 
 int attention_mma_supported(const AttnP& p) {
-  if (!p.qh || !p.oh || p.pesum) return 0;
+  if (!p.qh || !p.oh) return 0;
+  if (p.pesum) {  // PE variant: fp16 pesum, image rows as key tiles, head dims used at 1/32 resolution
+    if (!p.ph_half || p.pe_w > FA_BK || p.pe_h * p.pe_w != p.N || p.pe_h > 128) return 0;
+    if (!(p.d == 16 || p.d == 32 || p.d == 64 || p.d == 96)) return 0;
+  }
   if (p.qkv_ld % 8 || p.out_ld % 2 || !aligned(p.qkv, 16) || !aligned(p.out, 4)) return 0;
   switch (p.d) {
     case 16: case 32: case 64: case 96: case 128: case 192: case 256: return 1;
@@ -174,14 +253,22 @@ int attention_mma_supported(const AttnP& p) {
 }
 
 int attention_mma_launch(const AttnP& p, cudaStream_t s) {
+  if (p.pesum) {
+    switch (p.d) {
+      case 16: return launch_fa<16, true>(p, s);
+      case 32: return launch_fa<32, true>(p, s);
+      case 64: return launch_fa<64, true>(p, s);
+      case 96: return launch_fa<96, true>(p, s);
+    }
+  }
   switch (p.d) {
-    case 16: return launch_fa<16>(p, s);
-    case 32: return launch_fa<32>(p, s);
-    case 64: return launch_fa<64>(p, s);
-    case 96: return launch_fa<96>(p, s);
-    case 128: return launch_fa<128>(p, s);
-    case 192: return launch_fa<192>(p, s);
-    case 256: return launch_fa<256>(p, s);
+    case 16: return launch_fa<16, false>(p, s);
+    case 32: return launch_fa<32, false>(p, s);
+    case 64: return launch_fa<64, false>(p, s);
+    case 96: return launch_fa<96, false>(p, s);
+    case 128: return launch_fa<128, false>(p, s);
+    case 192: return launch_fa<192, false>(p, s);
+    case 256: return launch_fa<256, false>(p, s);
   }
   set_error("attention_mma: unsupported head dim %d", p.d);
   return -1;

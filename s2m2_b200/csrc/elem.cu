@@ -88,13 +88,16 @@ __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, dou
   }
 }
 
+// one warp per (n, g, k): lanes stride over the block partials, then a fixed shuffle tree -> deterministic
 __global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int groups, int N, double* __restrict__ stats) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g, k)
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * groups * 2) return;
   int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
   double acc = 0.0;
-  for (int b = 0; b < nblk; ++b) acc += part[(((long long)n * nblk + b) * groups + g) * 2 + k];
-  stats[i] = acc;
+  for (int b = lane; b < nblk; b += 32) acc += part[(((long long)n * nblk + b) * groups + g) * 2 + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) stats[i] = acc;
 }
 
 __global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const double* __restrict__ stats,
@@ -231,10 +234,10 @@ __global__ void gr_prep_kernel(const float* __restrict__ disp, const float* __re
 }
 
 __global__ void gr_merge_kernel(float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ upd,
-                                long long n, int pos) {
+                                long long upd_ld, long long n, int pos) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float m = conf[i] > 0.2f ? 1.f : 0.f;
-    float d = m * disp[i] + (1.f - m) * upd[i];
+    float d = m * disp[i] + (1.f - m) * upd[i * upd_ld];
     disp[i] = pos ? fmaxf(d, 0.f) : d;
   }
 }
@@ -246,15 +249,16 @@ __global__ void lr_prep_kernel(const float* __restrict__ disp, const float* __re
 }
 
 __global__ void lr_update_kernel(float* __restrict__ disp, float* __restrict__ conf, float* __restrict__ occ,
-                                 const float4* __restrict__ small, const float* __restrict__ dd, const float* __restrict__ co,
+                                 const float4* __restrict__ small, const float* __restrict__ upd, long long upd_ld,
                                  long long n, int w, int pos) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float4 s = small[i];
-    float d = disp[i] + dd[i];
+    const float* u = upd + i * upd_ld;   // [delta disp, delta conf logit, delta occ logit, ...]
+    float d = disp[i] + u[0];
     if (pos) d = fmaxf(d, 0.f);
     float x = (float)(i % w);
-    conf[i] = 1.f / (1.f + expf(-(co[2 * i] + s.y)));
-    float o = 1.f / (1.f + expf(-(co[2 * i + 1] + s.z)));
+    conf[i] = 1.f / (1.f + expf(-(u[1] + s.y)));
+    float o = 1.f / (1.f + expf(-(u[2] + s.z)));
     occ[i] = (x - d >= 0.f) ? o : 0.f;
     disp[i] = d;
   }
@@ -300,7 +304,7 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
   S2M2_CHECK(smem <= 48 * 1024, "groupnorm: C=%d too large", x->C);
   gn_stats_kernel<<<grid, 256, smem, s>>>(tv(*x), HW, groups, ppb, part);
   S2M2_LAUNCH_OK("gn_stats");
-  gn_final_kernel<<<cdiv(2LL * x->N * groups, 128), 128, 0, s>>>(part, nblk, groups, x->N, stats);
+  gn_final_kernel<<<cdiv(2LL * x->N * groups * 32, 128), 128, 0, s>>>(part, nblk, groups, x->N, stats);
   S2M2_LAUNCH_OK("gn_final");
   long long total4 = npix(*x) * (x->C / 4);
   gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, stats, gamma, beta, total4);
@@ -397,8 +401,10 @@ int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n
   return 0;
 }
 
-int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t n, int32_t pos, void* stream) {
-  gr_merge_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, upd, n, pos);
+int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t upd_ld, int64_t n, int32_t pos,
+                                  void* stream) {
+  S2M2_CHECK(upd_ld >= 1, "global_refiner_merge: bad upd_ld");
+  gr_merge_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, upd, upd_ld, n, pos);
   S2M2_LAUNCH_OK("global_refiner_merge");
   return 0;
 }
@@ -410,10 +416,11 @@ int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const floa
   return 0;
 }
 
-int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* dd, const float* co,
+int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* upd, int64_t upd_ld,
                                   int32_t B, int32_t h, int32_t w, int32_t pos, void* stream) {
   long long n = (long long)B * h * w;
-  lr_update_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, (const float4*)small, dd, co, n, w, pos);
+  S2M2_CHECK(upd_ld >= 3, "local_refiner_update: upd needs >= 3 channels");
+  lr_update_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, (const float4*)small, upd, upd_ld, n, w, pos);
   S2M2_LAUNCH_OK("local_refiner_update");
   return 0;
 }

@@ -163,6 +163,21 @@ class S2M2(nn.Module):
         w = self._w(name + ".weight")
         return self._mk(w.flip(2, 3).permute(1, 0, 2, 3).contiguous(), self._w(name + ".bias"), name=name)
 
+    def _head_pad(self):
+        """Tiny-Cout heads (C -> 1/2/3, K = 9C) are GEMV-like: on the tcgen05 path they run as one 64-wide tile
+        (zero weights for the padding); in fp32 mode the CUDA-core kernel takes them unpadded."""
+        return 64 if self.precision == "fp16" else None
+
+    def _pack_update_heads(self, r, C):
+        """disp_update.2 (C->1) and conf_occ_update.2 (C->2), both bias-free 3x3 (refinenet.py:115-122), as ONE conv over
+        the fused hidden tensor [disp hidden (C) | conf/occ hidden (C)] with block-structured weights -> 3 channels."""
+        wd = self._w(f"{r}.disp_update.2.weight")          # (1, C, 3, 3)
+        wc = self._w(f"{r}.conf_occ_update.2.weight")      # (2, C, 3, 3)
+        w = torch.zeros(3, 2 * C, 3, 3, device=wd.device)
+        w[0:1, :C] = wd
+        w[1:3, C:] = wc
+        return self._mk(w, None, name=f"{r}.update_heads", cout_to=self._head_pad())
+
     def _pack_attn(self, p, heads, pe=False):
         q, k, v = self._lin(p + ".q"), self._lin(p + ".k"), self._lin(p + ".v")
         d = {"qkv": self._cat_out([q, k, v], p + ".qkv"), "proj": self._lin(p + ".proj"), "heads": heads}
@@ -244,7 +259,7 @@ class S2M2(nn.Module):
         out_b = self._w(f"{g}.out_feat.0.bias") * 1e2
         P["gr"] = {"i0": self._mk(wpad, self._w(f"{g}.init_feat.0.bias"), name=f"{g}.init_feat.0"),
                    "i2": self._conv(f"{g}.init_feat.2"), "unet": self._pack_unet(f"{g}.refine_unet", 1, False),
-                   "out": self._mk(out_w, out_b, name=f"{g}.out_feat.0")}
+                   "out": self._mk(out_w, out_b, name=f"{g}.out_feat.0", cout_to=self._head_pad())}
         P["ffl"] = self._pack_fusion("feat_fusion_layer")
         P["ctx0"], P["ctx2"] = self._conv("ctx_feat.0"), self._conv("ctx_feat.2")
         r = "refiner"
@@ -256,7 +271,7 @@ class S2M2(nn.Module):
                    "unet": self._pack_unet(f"{r}.refine_unet", 1, False),
                    "upd0": self._cat_out([self._conv(f"{r}.disp_update.0"), self._conv(f"{r}.conf_occ_update.0")],
                                          f"{r}.upd0"),
-                   "du2": self._conv(f"{r}.disp_update.2"), "cu2": self._conv(f"{r}.conf_occ_update.2"),
+                   "upd2": self._pack_update_heads(r, C),
                    "zr1": self._cat_out([self._conv(f"{r}.gru.convz1", ph=1, pw=0), self._conv(f"{r}.gru.convr1", ph=1, pw=0)], "zr1"),
                    "q1": self._conv(f"{r}.gru.convq1", ph=1, pw=0),
                    "zr2": self._cat_out([self._conv(f"{r}.gru.convz2", ph=0, pw=1), self._conv(f"{r}.gru.convr2", ph=0, pw=1)], "zr2"),
@@ -522,9 +537,8 @@ class S2M2(nn.Module):
                 qt = self._c(rhx, q, ACT_TANH)
                 ops.gru_update(zrt[..., :C], qt, hidden)                    # hidden = (1-z) h + z q, in place
             t = self._c(hidden, lr["upd0"], ACT_GELU)
-            dd = self._c(t[..., :C], lr["du2"], out_dtype=f32)
-            co = self._c(t[..., C:], lr["cu2"], out_dtype=f32)
-            ops.local_refiner_update(disp, conf, occ, small, dd, co, self.use_positivity)
+            upd = self._c(t, lr["upd2"], out_dtype=f32)                    # [d disp | d conf logit | d occ logit | pad]
+            ops.local_refiner_update(disp, conf, occ, small, upd, self.use_positivity)
             if self.taps is not None:
                 self.taps[f"refiner.{it}.disp"] = disp.clone().unsqueeze(1)
                 self.taps[f"refiner.{it}.conf"] = conf.clone().unsqueeze(1)

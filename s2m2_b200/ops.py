@@ -246,22 +246,22 @@ class CudaOps:
         if upd.dtype != torch.float32 or not upd.is_contiguous():
             raise ValueError("global_refiner_merge: update must be contiguous fp32")
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_global_refiner_merge(p(disp), p(conf), p(upd), C.c_int64(disp.numel()),
-                                                         int(use_positivity), self._stream()), "global_refiner_merge")
+        self._chk(self.lib.s2m2b200_global_refiner_merge(p(disp), p(conf), p(upd), C.c_int64(upd.shape[3]),
+                                                         C.c_int64(disp.numel()), int(use_positivity), self._stream()),
+                  "global_refiner_merge")
 
     def local_refiner_prep(self, disp, conf, occ, small):
         p = lambda t: C.c_void_p(t.data_ptr())
         self._chk(self.lib.s2m2b200_local_refiner_prep(p(disp), p(conf), p(occ), C.c_int64(disp.numel()), p(small),
                                                        self._stream()), "local_refiner_prep")
 
-    def local_refiner_update(self, disp, conf, occ, small, dd, co, use_positivity):
+    def local_refiner_update(self, disp, conf, occ, small, upd, use_positivity):
         B, h, w = disp.shape
-        for t in (dd, co):
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("local_refiner_update: head outputs must be contiguous fp32")
+        if upd.dtype != torch.float32 or not upd.is_contiguous() or upd.shape[3] < 3:
+            raise ValueError("local_refiner_update: head output must be contiguous fp32 with >= 3 channels")
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_local_refiner_update(p(disp), p(conf), p(occ), p(small), p(dd), p(co), B, h, w,
-                                                         int(use_positivity), self._stream()), "local_refiner_update")
+        self._chk(self.lib.s2m2b200_local_refiner_update(p(disp), p(conf), p(occ), p(small), p(upd), C.c_int64(upd.shape[3]),
+                                                         B, h, w, int(use_positivity), self._stream()), "local_refiner_update")
 
     # -- upsampling
     def upsample4x_convex(self, disp, occ, conf, logits, up):

@@ -128,6 +128,8 @@ ATTN_CASES = [
     (4, 33, 4, 16, True, None),
     (2, 6 * 7, 8, 8, False, (6, 7)),
     (2, 5 * 9, 8, 32, False, (5, 9)),
+    (2, 15 * 20, 8, 32, False, (15, 20)),       # S@640x480 pyramid PE block
+    (2, 32 * 38, 8, 64, False, (32, 38)),       # L@1216x1024 pyramid PE block
     (2, 100, 8, 4, False, None),
     (3, 70, 1, 256, False, None),
     (2, 50, 2, 96, True, None),
@@ -279,7 +281,7 @@ def test_cv_lookup_and_refiner_glue(ops):
         cu.global_refiner_prep(disp, conf, oa[..., 32:34])
         th.global_refiner_prep(disp, conf, ob[..., 32:34])
         _close(oa, ob, 1e-5 if dtype == torch.float32 else 2e-3, 1e-6 if dtype == torch.float32 else 2e-3, "gr_prep")
-    upd = _rand((B, h, w, 1), torch.float32, g, 10.0)
+    upd = _rand((B, h, w, 4), torch.float32, g, 10.0)
     da, db = disp.clone(), disp.clone()
     cu.global_refiner_merge(da, conf, upd, True)
     th.global_refiner_merge(db, conf, upd, True)
@@ -288,11 +290,11 @@ def test_cv_lookup_and_refiner_glue(ops):
     cu.local_refiner_prep(disp, conf, occ, sa)
     th.local_refiner_prep(disp, conf, occ, sb)
     _close(sa, sb, 2e-6, 2e-6, "lr_prep")
-    dd, co = _rand((B, h, w, 1), torch.float32, g), _rand((B, h, w, 2), torch.float32, g)
+    upd3 = _rand((B, h, w, 8), torch.float32, g)
     xa = [t.clone() for t in (disp, conf, occ)]
     xb = [t.clone() for t in (disp, conf, occ)]
-    cu.local_refiner_update(*xa, sa, dd, co, True)
-    th.local_refiner_update(*xb, sb, dd, co, True)
+    cu.local_refiner_update(*xa, sa, upd3, True)
+    th.local_refiner_update(*xb, sb, upd3, True)
     for u, v, nm in zip(xa, xb, ("disp", "conf", "occ")):
         _close(u, v, 2e-6, 2e-6, "lr_update " + nm)
     # the occlusion mask (s2m2.py:179) is a hard decision: identical zero pattern

@@ -194,14 +194,14 @@ class TorchOps:
         small[..., 2] = occ.logit(eps=1e-2)
         small[..., 3] = 0
 
-    def local_refiner_update(self, disp, conf, occ, small, dd, co, use_positivity):
-        d = disp + dd[..., 0].float()
+    def local_refiner_update(self, disp, conf, occ, small, upd, use_positivity):
+        d = disp + upd[..., 0].float()
         if use_positivity:
             d = d.clamp(min=0)
         w = disp.shape[-1]
         xs = torch.arange(w, dtype=torch.float32, device=disp.device).reshape(1, 1, w)
-        conf.copy_(torch.sigmoid(co[..., 0].float() + small[..., 1]))
-        occ.copy_(torch.sigmoid(co[..., 1].float() + small[..., 2]) * (xs - d >= 0))
+        conf.copy_(torch.sigmoid(upd[..., 1].float() + small[..., 1]))
+        occ.copy_(torch.sigmoid(upd[..., 2].float() + small[..., 2]) * (xs - d >= 0))
         disp.copy_(d)
 
     # upsampling
