@@ -425,11 +425,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         valid = py < p.Ho && px < p.Wo;
         opix = ((long long)img * p.Ho + py) * p.Wo + px;
       }
+      // the residual does not depend on the accumulator: fetch this warp's slice before waiting for the MMAs
+      constexpr int NCH = CG / 16;                       // 16-column chunks per warp
+      uint4 rpre[NCH][2];
+      const bool has_res = p.res != nullptr && !p.shuffle;
+      if (has_res && valid && p.rh) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int n = n0 + half * CG + c * 16;
+          if (n < p.Cout) {
+            const uint4* rp = (const uint4*)((const __half*)p.res + opix * p.res_ld + n);
+            rpre[c][0] = __ldg(rp);
+            rpre[c][1] = __ldg(rp + 1);
+          }
+        }
+      }
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = half * CG; c0 < (half + 1) * CG; c0 += 16) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int c0 = half * CG + c * 16;
         const int n = n0 + c0;
         if (n >= p.Cout) break;
         uint32_t rr[16];
@@ -459,12 +475,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           off = pix * p.y_ld + co;
         } else {
           off = opix * p.y_ld + n;
-          if (p.res) {
-            const long long ro = opix * p.res_ld + n;
+          if (has_res) {
+            if (p.rh) {
+              const __half2* hr = (const __half2*)&rpre[c][0];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 t = ld4(p.res, ro + i, p.rh);
-              v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+              for (int i = 0; i < 8; ++i) {
+                const float2 f = __half22float2(hr[i]);
+                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+              }
+            } else {
+              const long long ro = opix * p.res_ld + n;
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 t = ld4(p.res, ro + i, 0);
+                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+              }
             }
           }
         }
@@ -546,7 +571,7 @@ int conv_tc_supported(const S2m2Conv* a) {
   if (a->shuffle2x2) {
     if ((a->Cout / 4) % 16) return 0;
   } else if (res.ptr) {
-    if (res.ld % 4 || !aligned(res.ptr, res.dtype == S2M2_F16 ? 8 : 16)) return 0;
+    if (res.ld % 8 || !aligned(res.ptr, 16)) return 0;
   }
   if ((long long)x.N * x.H * x.W < 256) return 0;   // tiny problems: launch-bound either way
   return tc_device_ok() ? 1 : 0;
@@ -654,7 +679,10 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
     maps.act[2] = maps.act[0];
     maps.act[3] = maps.act[0];
   }
-  const int BN = a->Cout >= 256 ? 256 : (a->Cout >= 128 ? 128 : 64);
+  // N tile: as wide as Cout allows (fewest re-reads of the activations) unless that leaves SMs idle — small
+  // problems (1/16, 1/32 resolution) take narrower tiles so that ~every SM gets one.
+  int BN = a->Cout >= 256 ? 256 : (a->Cout >= 128 ? 128 : 64);
+  while (BN > 64 && mtiles * cdiv(a->Cout, BN) < 120) BN /= 2;
   {
     const long long K = (long long)p.taps * (x.C + (x2.ptr ? x2.C : 0));
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Cout}, strides[1] = {(cuuint64_t)K * 2};
