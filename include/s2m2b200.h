@@ -105,6 +105,15 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W,
                         const S2m2Tensor* out, void* stream);
 
+/* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images -> (2B,H,W,16)
+ * (s2m2.py:86-87, submodules.py:70-72,89).  w0 (16,3), w1 (16,16), biases (16), all fp32. */
+int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const S2m2Tensor* out, void* stream);
+/* Fused UpsampleMask1x inputs (submodules.py:121-124,138-139): out[...,0:16] = relu(convT3x3(up[...,0])),
+ * out[...,16:32] = relu(convT3x3(rgb)); wd (16,9) / wr (16,27) are the equivalent flipped conv weights, tap-major. */
+int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* wd, const float* bd, const float* wr,
+                           const float* br, const S2m2Tensor* out, void* stream);
+
 /* Dust-bin log-Sinkhorn + argmax + 5-tap soft-argmax over the (B,h,w,w) fp32 cost volume
  * (submodules.py:147-243): disp/conf/occ (B,h,w) fp32, amax int32 = prob_max_ind (submodules.py:226). */
 int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t w, float* disp, float* conf,
@@ -126,11 +135,12 @@ int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const fl
                                   int64_t upd_ld, int32_t B, int32_t h, int32_t w, int32_t use_positivity, void* stream);
 
 /* RAFT convex 4x upsampling of disp*4 | occ | conf with one set of 9 logits (s2m2.py:101-114,184-187):
- * logits (B,4h,4w,9) fp32 -> up (B,4h,4w,4) fp32 (4th channel 0). */
+ * logits (B,4h,4w,logits_ld >= 9) fp32, first 9 channels used -> up (B,4h,4w,4) fp32 (4th channel 0). */
 int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits,
-                               int32_t B, int32_t h, int32_t w, float* up, void* stream);
+                               int32_t logits_ld, int32_t B, int32_t h, int32_t w, float* up, void* stream);
 /* 9-tap softmax filter at full resolution (s2m2.py:116-133,190-193): out (3,B,1,H,W) planar fp32. */
-int s2m2b200_filter1x(const float* up, const float* logits, int32_t B, int32_t H, int32_t W, float* out, void* stream);
+int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
+                      void* stream);
 
 const char* s2m2b200_last_error(void);
 /* Version / capability string, e.g. "s2m2b200 0.1 sm_100a tcgen05". */

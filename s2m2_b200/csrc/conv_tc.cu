@@ -560,7 +560,7 @@ int conv_tc_supported(const S2m2Conv* a) {
   if (x.C % TC_BK || x.ld % 8 || !aligned(x.ptr, 16)) return 0;
   if (x2.ptr && (x2.C % TC_BK || x2.ld % 8 || !aligned(x2.ptr, 16))) return 0;
   if (!aligned(a->w, 16) || (a->bias && !aligned(a->bias, 16))) return 0;
-  if (a->Cout % 16 || a->Cout < 64) return 0;
+  if (a->Cout % 16 || a->Cout < 16) return 0;   // narrow heads still use a 64-wide tile (TMA zero-fills the missing rows)
   // same-size convolutions only (pad = k/2) or 1x1
   if (a->stride == 1) {
     const int Ho = x.H + 2 * a->pad_h - a->KH + 1, Wo = x.W + 2 * a->pad_w - a->KW + 1;

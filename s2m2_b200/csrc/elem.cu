@@ -68,15 +68,18 @@ __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, dou
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = lane; c < C; c += 32) {
-    float s = 0.f, q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {   // 4 channels per lane: 8/16-byte loads, a warp covers 128 channels of a pixel
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     for (int pp = p0 + wid; pp < p1; pp += nw) {
-      float v = ld1(x.p, ((long long)n * HW + pp) * x.ld + c, x.half);
-      s += v;
-      q += v * v;
+      const float4 v = ld4(x.p, ((long long)n * HW + pp) * x.ld + c, x.half);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
     }
-    sh[(wid * C + c) * 2 + 0] = s;
-    sh[(wid * C + c) * 2 + 1] = q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sh[(wid * C + c + k) * 2 + 0] = s[k];
+      sh[(wid * C + c + k) * 2 + 1] = q[k];
+    }
   }
   __syncthreads();
   if (threadIdx.x < 2 * groups) {
@@ -89,21 +92,32 @@ __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, dou
 }
 
 // one warp per (n, g, k): lanes stride over the block partials, then a fixed shuffle tree -> deterministic
-__global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int groups, int N, double* __restrict__ stats) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= N * groups * 2) return;
-  int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
-  double acc = 0.0;
-  for (int b = lane; b < nblk; b += 32) acc += part[(((long long)n * nblk + b) * groups + g) * 2 + k];
+// stats out: float2 (mean, rstd) per (n, g), computed once in double
+__global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int groups, int N, double cnt, float2* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // (n, g)
+  if (i >= N * groups) return;
+  const int g = i % groups, n = i / groups;
+  double s = 0.0, q = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    s += part[(((long long)n * nblk + b) * groups + g) * 2 + 0];
+    q += part[(((long long)n * nblk + b) * groups + g) * 2 + 1];
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) stats[i] = acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    stats[i] = make_float2((float)mean, rsqrtf((float)var + 1e-5f));
+  }
 }
 
-__global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const double* __restrict__ stats,
+__global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const float2* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, long long total4) {
   const int C = x.C, C4 = C / 4, cpg = C / groups;
-  const double cnt = (double)HW * cpg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long pix = i / C4;
     int c = (int)(i - pix * C4) * 4;
@@ -112,12 +126,8 @@ __global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const double* __
     float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int g = (c + k) / cpg;
-      double s = stats[((long long)n * groups + g) * 2], q = stats[((long long)n * groups + g) * 2 + 1];
-      double mean = s / cnt;
-      double var = q / cnt - mean * mean;
-      float rstd = rsqrtf((float)(var > 0 ? var : 0) + 1e-5f);
-      o[k] = (o[k] - (float)mean) * rstd * gamma[c + k] + beta[c + k];
+      const float2 mr = __ldg(stats + (long long)n * groups + (c + k) / cpg);
+      o[k] = (o[k] - mr.x) * mr.y * gamma[c + k] + beta[c + k];
     }
     st4(y.p, pix * y.ld + c, y.half, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -217,6 +227,89 @@ __global__ void preprocess_kernel(const float* __restrict__ left, const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused full-resolution tiny-channel layers (thread per pixel; weights in shared memory)
+// ------------------------------------------------------------------------------------------------
+// stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16)   (s2m2.py:86-87, submodules.py:70-72)
+__global__ void stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
+                            const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                            const float* __restrict__ b1, TV o) {
+  __shared__ float sw0[48], sb0[16], sw1[256], sb1[16];
+  for (int i = threadIdx.x; i < 48; i += blockDim.x) sw0[i] = w0[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sw1[i] = w1[i];
+  if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
+  __syncthreads();
+  const long long HW = (long long)H * W, total = 2LL * B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / HW, hw = i - n * HW;
+    const float* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
+    float x[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = (src[c * HW + hw] / 255.f - 0.5f) * 2.f;
+    float hdn[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float t = sb0[j] + sw0[j * 3] * x[0] + sw0[j * 3 + 1] * x[1] + sw0[j * 3 + 2] * x[2];
+      hdn[j] = 0.5f * t * (1.0f + erff(t * 0.70710678118654752440f));
+    }
+    float out[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float t = sb1[k];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t = fmaf(sw1[k * 16 + j], hdn[j], t);
+      out[k] = t;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) st4(o.p, i * o.ld + k, o.half, make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]));
+  }
+}
+
+// UpsampleMask1x inputs: relu(convT3x3(disp_up, 1->16)) | relu(convT3x3(rgb, 3->16))  (submodules.py:121-124,138-139)
+// weights are the equivalent (flipped) conv weights, tap-major: wd[co][tap], wr[co][tap*3 + ci]
+__global__ void mask1x_inputs_kernel(const float4* __restrict__ up, TV rgb, int B, int H, int W, const float* __restrict__ wd,
+                                     const float* __restrict__ bd, const float* __restrict__ wr, const float* __restrict__ br, TV o) {
+  __shared__ float swd[144], swr[432], sbd[16], sbr[16];
+  for (int i = threadIdx.x; i < 144; i += blockDim.x) swd[i] = wd[i];
+  for (int i = threadIdx.x; i < 432; i += blockDim.x) swr[i] = wr[i];
+  if (threadIdx.x < 16) { sbd[threadIdx.x] = bd[threadIdx.x]; sbr[threadIdx.x] = br[threadIdx.x]; }
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W);
+    long long t = i / W;
+    int Y = (int)(t % H);
+    long long b = t / H;
+    float dn[9], cn[27];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int tap = (dy + 1) * 3 + dx + 1;
+        const int yy = Y + dy, xx = X + dx;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const long long q = (b * H + yy) * W + xx;
+        dn[tap] = in ? up[q].x : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cn[tap * 3 + c] = in ? ld1(rgb.p, q * rgb.ld + c, rgb.half) : 0.f;
+      }
+    float out[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a = sbd[k], r = sbr[k];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) a = fmaf(swd[k * 9 + j], dn[j], a);
+#pragma unroll
+      for (int j = 0; j < 27; ++j) r = fmaf(swr[k * 27 + j], cn[j], r);
+      out[k] = fmaxf(a, 0.f);
+      out[16 + k] = fmaxf(r, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) st4(o.p, i * o.ld + k, o.half, make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // refiner glue on the 1/4-resolution scalar maps (fp32)
 // ------------------------------------------------------------------------------------------------
@@ -304,10 +397,11 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
   S2M2_CHECK(smem <= 48 * 1024, "groupnorm: C=%d too large", x->C);
   gn_stats_kernel<<<grid, 256, smem, s>>>(tv(*x), HW, groups, ppb, part);
   S2M2_LAUNCH_OK("gn_stats");
-  gn_final_kernel<<<cdiv(2LL * x->N * groups * 32, 128), 128, 0, s>>>(part, nblk, groups, x->N, stats);
+  gn_final_kernel<<<cdiv((long long)x->N * groups * 32, 128), 128, 0, s>>>(part, nblk, groups, x->N, (double)HW * (x->C / groups),
+                                                                           (float2*)stats);
   S2M2_LAUNCH_OK("gn_final");
   long long total4 = npix(*x) * (x->C / 4);
-  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, stats, gamma, beta, total4);
+  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, (const float2*)stats, gamma, beta, total4);
   S2M2_LAUNCH_OK("gn_apply");
   return 0;
 }
@@ -391,6 +485,24 @@ int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_
   S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 3, "preprocess: output must be (2B,H,W,3)");
   preprocess_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, tv(*out));
   S2M2_LAUNCH_OK("preprocess");
+  return 0;
+}
+
+int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
+  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 16 && vec4_ok(*out), "stem: output must be (2B,H,W,16), 4-aligned");
+  stem_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, w0, b0, w1, b1, tv(*out));
+  S2M2_LAUNCH_OK("stem");
+  return 0;
+}
+
+int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* wd, const float* bd, const float* wr,
+                           const float* br, const S2m2Tensor* out, void* stream) {
+  S2M2_CHECK(rgb->C == 3 && out->C == 32 && npix(*rgb) == npix(*out) && vec4_ok(*out) && aligned(up, 16),
+             "mask1x_inputs: rgb (B,H,W,3), out a 32-channel 4-aligned view, up 16-byte aligned");
+  mask1x_inputs_kernel<<<grid_for(npix(*out)), 256, 0, (cudaStream_t)stream>>>((const float4*)up, tv(*rgb), rgb->N, rgb->H, rgb->W,
+                                                                                  wd, bd, wr, br, tv(*out));
+  S2M2_LAUNCH_OK("mask1x_inputs");
   return 0;
 }
 

@@ -190,7 +190,7 @@ __device__ __forceinline__ void softmax9(const float* __restrict__ l, float* wt)
 }
 
 __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* __restrict__ occ, const float* __restrict__ conf,
-                                  const float* __restrict__ logits, int B, int h, int w, float4* __restrict__ up) {
+                                  const float* __restrict__ logits, int lld, int B, int h, int w, float4* __restrict__ up) {
   const int H = 4 * h, W = 4 * w;
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -199,7 +199,7 @@ __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* _
     int Y = (int)(t % H);
     long long b = t / H;
     float wt[9];
-    softmax9(logits + i * 9, wt);
+    softmax9(logits + i * lld, wt);
     int cy = Y >> 2, cx = X >> 2;
     float d = 0.f, o = 0.f, c = 0.f;
 #pragma unroll
@@ -217,7 +217,7 @@ __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* _
   }
 }
 
-__global__ void filter1x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int B, int H, int W,
+__global__ void filter1x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int lld, int B, int H, int W,
                                 float* __restrict__ out) {
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -226,7 +226,7 @@ __global__ void filter1x_kernel(const float4* __restrict__ up, const float* __re
     int Y = (int)(t % H);
     long long b = t / H;
     float wt[9];
-    softmax9(logits + i * 9, wt);
+    softmax9(logits + i * lld, wt);
     float d = 0.f, o = 0.f, c = 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy)
@@ -268,21 +268,22 @@ int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h,
   return 0;
 }
 
-int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits, int32_t B,
-                               int32_t h, int32_t w, float* up, void* stream) {
-  S2M2_CHECK(aligned(up, 16), "upsample4x_convex: up must be 16-byte aligned");
+int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits, int32_t logits_ld,
+                               int32_t B, int32_t h, int32_t w, float* up, void* stream) {
+  S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "upsample4x_convex: up must be 16-byte aligned, logits_ld >= 9");
   long long n = 16LL * B * h * w;
   long long g = (n + 255) / 256;
-  upsample4x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(disp, occ, conf, logits, B, h, w, (float4*)up);
+  upsample4x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(disp, occ, conf, logits, logits_ld, B, h, w, (float4*)up);
   S2M2_LAUNCH_OK("upsample4x_convex");
   return 0;
 }
 
-int s2m2b200_filter1x(const float* up, const float* logits, int32_t B, int32_t H, int32_t W, float* out, void* stream) {
-  S2M2_CHECK(aligned(up, 16), "filter1x: up must be 16-byte aligned");
+int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
+                      void* stream) {
+  S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "filter1x: up must be 16-byte aligned, logits_ld >= 9");
   long long n = (long long)B * H * W;
   long long g = (n + 255) / 256;
-  filter1x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, B, H, W, out);
+  filter1x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, logits_ld, B, H, W, out);
   S2M2_LAUNCH_OK("filter1x");
   return 0;
 }

@@ -149,10 +149,15 @@ class S2M2(nn.Module):
         return ConvW(w.contiguous(), torch.cat(bs).contiguous(), c0.kh, c0.kw, c0.stride, c0.ph, c0.pw, c0.cin,
                      sum(c.cout for c in convs), False, name)
 
-    def _convT2(self, name):
-        """ConvTranspose2d(k=2,s=2): weight (Cin,Cout,2,2) -> GEMM (4*Cout, Cin) + pixel-shuffle store."""
+    def _convT2(self, name, cout_to=None):
+        """ConvTranspose2d(k=2,s=2): weight (Cin,Cout,2,2) -> GEMM (4*Cout, Cin) + pixel-shuffle store.
+        ``cout_to`` zero-pads the output channels (9 -> 16 logits so the layer takes the tcgen05 path)."""
         w = self._w(name + ".weight")
         b = self._w(name + ".bias")
+        if cout_to is not None and cout_to > w.shape[1]:
+            pad = cout_to - w.shape[1]
+            w = torch.cat([w, w.new_zeros(w.shape[0], pad, 2, 2)], 1)
+            b = torch.cat([b, b.new_zeros(pad)])
         cin, cout = w.shape[:2]
         wg = w.permute(2, 3, 1, 0).reshape(4 * cout, cin)          # row = (a*2+b)*Cout + co
         c = self._mk(wg[:, :, None, None], b.repeat(4), shuffle=True, name=name)
@@ -165,8 +170,8 @@ class S2M2(nn.Module):
 
     def _head_pad(self):
         """Tiny-Cout heads (C -> 1/2/3, K = 9C) are GEMV-like: on the tcgen05 path they run as one 64-wide tile
-        (zero weights for the padding); in fp32 mode the CUDA-core kernel takes them unpadded."""
-        return 64 if self.precision == "fp16" else None
+        (zero weights for the padding); in fp32 mode the CUDA-core kernel takes them unpadded."""  # tile is 64 wide, 16 columns are stored
+        return 16 if self.precision == "fp16" else None
 
     def _pack_update_heads(self, r, C):
         """disp_update.2 (C->1) and conf_occ_update.2 (C->2), both bias-free 3x3 (refinenet.py:115-122), as ONE conv over
@@ -237,7 +242,9 @@ class S2M2(nn.Module):
         C, NTR = self.feature_channels, self.num_transformer
         P: Dict[str, object] = {}
         b = "cnn_backbone"
-        P["bb"] = {"c00": self._conv(f"{b}.conv0.0"), "c02": self._conv(f"{b}.conv0.2"),
+        f32c = lambda n: self._w(n).float().contiguous()
+        P["bb"] = {"w0": f32c(f"{b}.conv0.0.weight").reshape(16, 3).contiguous(), "b0": f32c(f"{b}.conv0.0.bias"),
+                   "w1": f32c(f"{b}.conv0.2.weight").reshape(16, 16).contiguous(), "b1": f32c(f"{b}.conv0.2.bias"),
                    "d0": self._conv(f"{b}.conv1_down.0", stride=2), "d2": self._conv(f"{b}.conv1_down.2"),
                    "gn_w": self._w(f"{b}.norm1.weight").float().contiguous(),
                    "gn_b": self._w(f"{b}.norm1.bias").float().contiguous(),
@@ -278,11 +285,14 @@ class S2M2(nn.Module):
                    "q2": self._conv(f"{r}.gru.convq2", ph=0, pw=1)}
         u = "upsample_mask_4x_refine"
         P["u4"] = {"x": self._convT2(f"{u}.conv_x"), "y": self._conv(f"{u}.conv_y"),
-                   "c0": self._conv(f"{u}.conv_concat.0"), "c2": self._convT2(f"{u}.conv_concat.2")}
+                   "c0": self._conv(f"{u}.conv_concat.0"), "c2": self._convT2(f"{u}.conv_concat.2", cout_to=16)}
         u = "upsample_mask_1x"
-        P["u1"] = {"disp": self._convT3(f"{u}.conv_disp.0"), "rgb": self._convT3(f"{u}.conv_rgb.0"),
+        wd = self._w(f"{u}.conv_disp.0.weight").flip(2, 3).permute(1, 2, 3, 0).reshape(16, 9)      # [co][tap]
+        wr = self._w(f"{u}.conv_rgb.0.weight").flip(2, 3).permute(1, 2, 3, 0).reshape(16, 27)     # [co][tap*3+ci]
+        P["u1"] = {"wd": wd.float().contiguous(), "bd": f32c(f"{u}.conv_disp.0.bias"),
+                   "wr": wr.float().contiguous(), "br": f32c(f"{u}.conv_rgb.0.bias"),
                    "ctx": self._convT2(f"{u}.conv_ctx"), "c0": self._conv(f"{u}.conv_concat.0", cin_to=64, cout_to=64),
-                   "c2": self._convT1(f"{u}.conv_concat.2", cin_to=64)}
+                   "c2": self._convT1(f"{u}.conv_concat.2", cin_to=64, cout_to=16)}
         return P
 
     def _ensure_packed(self, device):
@@ -446,12 +456,13 @@ class S2M2(nn.Module):
         h4, w4 = H // 4, W // 4
 
         # -- normalise + NCHW->NHWC; left and right stacked on the batch dim (s2m2.py:86-96)
-        img = ops.empty((2 * B, H, W, 3), adt, dev)
+        img = ops.empty((2 * B, H, W, 3), adt, dev)                      # normalised NHWC copy (mask head input)
         ops.preprocess(img0.float().contiguous(), img1.float().contiguous(), img)
 
         # -- CNN backbone (submodules.py:88-93)
         bb = P["bb"]
-        x = self._c(self._c(img, bb["c00"], ACT_GELU), bb["c02"])
+        x = ops.empty((2 * B, H, W, 16), adt, dev)
+        ops.stem(img0.float().contiguous(), img1.float().contiguous(), bb["w0"], bb["b0"], bb["w1"], bb["b1"], x)
         x = self._c(self._c(x, bb["d0"], ACT_GELU), bb["d2"])
         x2 = self._new(x, C)
         ops.groupnorm(x, 8, bb["gn_w"], bb["gn_b"], x2)
@@ -549,7 +560,7 @@ class S2M2(nn.Module):
         m4in = ops.empty((B, H // 2, W // 2, 128), adt, dev)
         self._c(hidden, u4["x"], out=m4in[..., :64])
         self._c(f2_0, u4["y"], out=m4in[..., 64:])
-        m4 = self._c(self._c(m4in, u4["c0"], ACT_RELU), u4["c2"], out_dtype=f32)   # (B,H,W,9) logits
+        m4 = self._c(self._c(m4in, u4["c0"], ACT_RELU), u4["c2"], out_dtype=f32)   # (B,H,W,16) logits, 9 used
         up = ops.empty((B, H, W, 4), f32, dev)                          # disp*4 | occ | conf | 0   (interleaved)
         ops.upsample4x_convex(disp, occ, conf, m4, up)
         if self.taps is not None:
@@ -559,8 +570,7 @@ class S2M2(nn.Module):
         # -- edge-guided 1x filter (submodules.py:137-145, s2m2.py:116-133,190-193)
         u1 = P["u1"]
         m1in = ops.zeros((B, H, W, 64), adt, dev)                       # disp 16 | rgb 16 | ctx 16 | 16 zero pad
-        self._c(up[..., 0:1], u1["disp"], ACT_RELU, out=m1in[..., 0:16])
-        self._c(img[:B], u1["rgb"], ACT_RELU, out=m1in[..., 16:32])
+        ops.mask1x_inputs(up, img[:B], u1["wd"], u1["bd"], u1["wr"], u1["br"], m1in[..., 0:32])
         self._c(f2_0, u1["ctx"], out=m1in[..., 32:48])
         m1 = self._c(self._c(m1in, u1["c0"], ACT_RELU), u1["c2"], out_dtype=f32)
         out = ops.empty((3, B, 1, H, W), f32, dev)

@@ -53,7 +53,7 @@ def load_library():
 EXPORTS = [
     "s2m2b200_conv2d", "s2m2b200_attention", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
-    "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
+    "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
     "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_last_error",
     "s2m2b200_version", "s2m2b200_launch_count",
@@ -223,6 +223,18 @@ class CudaOps:
         self._chk(self.lib.s2m2b200_preprocess(C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()), B, H, W,
                                                C.byref(ot), self._stream()), "preprocess")
 
+    def stem(self, left, right, w0, b0, w1, b1, out):
+        B, _, H, W = left.shape
+        ot = tview(out)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_stem(p(left), p(right), B, H, W, p(w0), p(b0), p(w1), p(b1), C.byref(ot), self._stream()), "stem")
+
+    def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
+        rt, ot = tview(rgb), tview(out)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_mask1x_inputs(p(up), C.byref(rt), p(wd), p(bd), p(wr), p(br), C.byref(ot), self._stream()),
+                  "mask1x_inputs")
+
     # -- matching
     def sinkhorn_softargmax(self, cv, disp, conf, occ, amax, use_positivity, iters):
         B, h, w, _ = cv.shape
@@ -266,15 +278,15 @@ class CudaOps:
     # -- upsampling
     def upsample4x_convex(self, disp, occ, conf, logits, up):
         B, h, w = disp.shape
-        if logits.dtype != torch.float32 or not logits.is_contiguous():
-            raise ValueError("upsample4x_convex: logits must be contiguous fp32 (B,4h,4w,9)")
+        if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.shape[3] < 9:
+            raise ValueError("upsample4x_convex: logits must be contiguous fp32 (B,4h,4w,>=9)")
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_upsample4x_convex(p(disp), p(occ), p(conf), p(logits), B, h, w, p(up),
+        self._chk(self.lib.s2m2b200_upsample4x_convex(p(disp), p(occ), p(conf), p(logits), logits.shape[3], B, h, w, p(up),
                                                       self._stream()), "upsample4x_convex")
 
     def filter1x(self, up, logits, out):
         B, H, W, _ = up.shape
-        if logits.dtype != torch.float32 or not logits.is_contiguous():
-            raise ValueError("filter1x: logits must be contiguous fp32 (B,H,W,9)")
+        if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.shape[3] < 9:
+            raise ValueError("filter1x: logits must be contiguous fp32 (B,H,W,>=9)")
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), B, H, W, p(out), self._stream()), "filter1x")
+        self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), logits.shape[3], B, H, W, p(out), self._stream()), "filter1x")

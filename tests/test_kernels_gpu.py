@@ -306,7 +306,7 @@ def test_convex_upsampling(ops):
     g = torch.Generator().manual_seed(10)
     B, h, w = 2, 5, 7
     disp, occ, conf = (torch.rand((B, h, w), generator=g).to(DEV) * s for s in (30, 1, 1))
-    logits = _rand((B, 4 * h, 4 * w, 9), torch.float32, g, 2.0)
+    logits = _rand((B, 4 * h, 4 * w, 16), torch.float32, g, 2.0)     # 9 logits + 7 pad channels (ld = 16)
     ua, ub = torch.zeros((B, 4 * h, 4 * w, 4), device=DEV), torch.zeros((B, 4 * h, 4 * w, 4), device=DEV)
     cu.upsample4x_convex(disp, occ, conf, logits, ua)
     th.upsample4x_convex(disp, occ, conf, logits, ub)
@@ -316,3 +316,29 @@ def test_convex_upsampling(ops):
     cu.filter1x(ub, l1, oa)
     th.filter1x(ub, l1, ob)
     _close(oa, ob, 2e-6, 2e-5, "filter1x")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_fused_stem_and_mask1x_inputs(ops, dtype):
+    cu, th = ops
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 2, 10, 14
+    l = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
+    r = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
+    w0, b0 = _rand((16, 3), torch.float32, g, 0.5), _rand((16,), torch.float32, g, 0.5)
+    w1, b1 = _rand((16, 16), torch.float32, g, 0.25), _rand((16,), torch.float32, g, 0.25)
+    a = torch.zeros((2 * B, H, W, 16), dtype=dtype, device=DEV)
+    b = torch.zeros_like(a)
+    cu.stem(l, r, w0, b0, w1, b1, a)
+    th.stem(l, r, w0, b0, w1, b1, b)
+    tol = (2e-5, 2e-5) if dtype == torch.float32 else (3e-3, 3e-3)
+    _close(a, b, *tol, "stem")
+    up = _rand((B, H, W, 4), torch.float32, g, 20.0)
+    rgb = _rand((B, H, W, 3), dtype, g)
+    wd, bd = _rand((16, 9), torch.float32, g, 0.3), _rand((16,), torch.float32, g, 0.3)
+    wr, br = _rand((16, 27), torch.float32, g, 0.2), _rand((16,), torch.float32, g, 0.2)
+    oa = torch.zeros((B, H, W, 64), dtype=dtype, device=DEV)
+    ob = torch.zeros_like(oa)
+    cu.mask1x_inputs(up, rgb, wd, bd, wr, br, oa[..., 0:32])
+    th.mask1x_inputs(up, rgb, wd, bd, wr, br, ob[..., 0:32])
+    _close(oa, ob, *((2e-5, 2e-4) if dtype == torch.float32 else (3e-3, 3e-2)), "mask1x_inputs")

@@ -30,6 +30,17 @@ def test_schedule_matches_golden(name):
     d, o, c = m(left, right)
     assert d.shape == (cfg["B"], 1, cfg["H"], cfg["W"]) and d.dtype == torch.float32
     assert (m.taps["disp_init.cv"] - g["tap:disp_init#0.3"]).abs().max() < 2e-3
+    if not cfg["pos"]:
+        # un-masked matching with random-init weights has exact near-ties: an arg-max flip is legitimate iff the
+        # reference's own top-1/top-2 margin there is at rounding level (see tests/test_parity_gpu.py)
+        ot = {}
+        O.forward(sd, left, right, cfg["NTR"], cfg["pos"], cfg["it"], ot)
+        top2 = ot["disp_init.prob"].topk(2, dim=3).values
+        margin = (top2[..., 0] - top2[..., 1]) / top2[..., 0].clamp(min=1e-30)
+        flips = m.taps["disp_init.argmax"] != ot["disp_init.argmax"]
+        assert flips.float().mean() < 0.02 and ((not flips.any()) or float(margin[flips].max()) < 1e-4)
+        assert (d - g["disp"]).abs().median() < 1e-4
+        return
     assert (m.taps["disp_init.disp"] - g["tap:disp_init#0.0"]).abs().max() < 1e-3
     assert (d - g["disp"]).abs().max() < 2e-3
     assert (d - g["disp"]).abs().mean() < 5e-5

@@ -122,6 +122,18 @@ class TorchOps:
         x = torch.cat([left, right], 0)
         out.copy_(((x / 255.0 - 0.5) * 2).permute(0, 2, 3, 1).to(out.dtype))
 
+    def stem(self, left, right, w0, b0, w1, b1, out):
+        x = ((torch.cat([left, right], 0) / 255.0 - 0.5) * 2)
+        h = F.gelu(F.conv2d(x, w0[:, :, None, None], b0))
+        out.copy_(F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1).to(out.dtype))
+
+    def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
+        d = up[..., 0:1].float().permute(0, 3, 1, 2)
+        a = F.relu(F.conv2d(d, wd.reshape(16, 3, 3, 1).permute(0, 3, 1, 2), bd, padding=1))
+        r = F.relu(F.conv2d(rgb.float().permute(0, 3, 1, 2), wr.reshape(16, 3, 3, 3).permute(0, 3, 1, 2), br, padding=1))
+        out[..., 0:16] = a.permute(0, 2, 3, 1).to(out.dtype)
+        out[..., 16:32] = r.permute(0, 2, 3, 1).to(out.dtype)
+
     # matching
     def sinkhorn_softargmax(self, cv, disp, conf, occ, amax, use_positivity, iters):
         B, h, w, _ = cv.shape
@@ -213,13 +225,13 @@ class TorchOps:
 
     def upsample4x_convex(self, disp, occ, conf, logits, up):
         B, h, w = disp.shape
-        wts = logits.float().permute(0, 3, 1, 2).softmax(dim=1)
+        wts = logits[..., :9].float().permute(0, 3, 1, 2).softmax(dim=1)
         for c, m in enumerate((disp * 4, occ, conf)):
             xu = F.interpolate(self._unfold(m.unsqueeze(1)), (4 * h, 4 * w), mode="nearest")
             up[..., c] = (xu * wts).sum(1)
         up[..., 3] = 0
 
     def filter1x(self, up, logits, out):
-        wts = logits.float().permute(0, 3, 1, 2).softmax(dim=1)
+        wts = logits[..., :9].float().permute(0, 3, 1, 2).softmax(dim=1)
         for c in range(3):
             out[c] = (self._unfold(up[..., c].unsqueeze(1)) * wts).sum(1, keepdim=True)
