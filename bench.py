@@ -294,8 +294,16 @@ def main():
             kms = k0.elapsed_time(k1) / reps
             pk = _peaks()
             ach = flops / (kms * 1e-3) / 1e12
+            traffic = None   # dram read+write bytes per launch of this kernel, from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", "r1_conv_tc_traffic.json")
+            Mrows = o.shape[0] * o.shape[1] * o.shape[2]
+            if os.path.exists(tpath):
+                for kname, kv in json.load(open(tpath))["kernels"].items():
+                    if f"M={Mrows} N={cw.cout} K={cw.kh * cw.kw * cw.cin}" in kname:
+                        traffic = kv["dram_read_bytes"] + kv["dram_write_bytes"]
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": ach / pk["tensor_burst"],
-                    "traffic": None, "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
+                    "traffic": traffic, "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch, profiles/r1_conv_tc_ncu.md",
+                    "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
                     "kernel": f"implicit-GEMM conv {cw.name}: M={o.shape[0] * o.shape[1] * o.shape[2]} N={cw.cout} K={cw.kh * cw.kw * cw.cin}",
                     "kernel_ms": kms, "kernel_gflop": flops / 1e9, "conv_gflop_per_step": total_conv_flops / 1e9}
 
