@@ -7,7 +7,12 @@
 
 namespace s2m2 {
 
-constexpr int FA_BQ = 64, FA_BK = 64, FA_THREADS = 128;
+constexpr int FA_BQ = 64, FA_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;  // src-size 0 -> 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -31,7 +36,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 //     pesum[q, 16:32] = .5 * sum_yj  My[q, yj] * pe_y[yq - yj + h - 1],   My[q, yj] = sum_xj P[q, (yj, xj)]
 // only needs the two marginals of P: Mx accumulates in registers (a thread always owns the same key columns),
 // My is one row-sum per tile.  The (N, N, 32) tensor of utils.py:32-60 never exists.
-template <int D, bool PE>
+template <int D, int FA_BK, bool PE>
 __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   constexpr int LDS = D + 8;               // padded row (halves): conflict-free ldmatrix
   constexpr int KS = D / 16;               // k-steps of QK^T
@@ -39,9 +44,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   constexpr int OG = D / 8;                // 8-channel groups of the output
   extern __shared__ __align__(16) __half sm[];
   __half* Qs = sm;                         // [FA_BQ][LDS]
-  __half* Ks = Qs + FA_BQ * LDS;           // [FA_BK][LDS]
-  __half* Vs = Ks + FA_BK * LDS;           // [FA_BK][LDS]
-  float* My_raw = (float*)(Vs + FA_BK * LDS);   // PE: [FA_BQ][pe_h] row sums at the running max of that time
+  __half* KV = Qs + FA_BQ * LDS;           // 2 stages x { K [FA_BK][LDS], V [FA_BK][LDS] }  (cp.async double buffer)
+  constexpr int STAGE = 2 * FA_BK * LDS;   // halves per stage
+  float* My_raw = (float*)(KV + 2 * STAGE);     // PE: [FA_BQ][pe_h] row sums at the running max of that time
   float* M_at = My_raw + FA_BQ * (PE ? p.pe_h : 0);   // PE: [FA_BQ][pe_h] that running max
   float* Mxs = M_at + FA_BQ * (PE ? p.pe_h : 0);      // PE: [FA_BQ][FA_BK] x-marginal (written at the end)
   const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, s = blockIdx.z;
@@ -63,8 +68,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;   // rows g and g+8 of this warp's 16-row slab
   const float sl2 = p.scale * 1.4426950408889634f;       // softmax in base 2
   const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
-  const uint32_t k_addr = (uint32_t)__cvta_generic_to_shared(Ks + ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8);
-  const uint32_t v_addr = (uint32_t)__cvta_generic_to_shared(Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+  const uint32_t k_addr0 = (uint32_t)__cvta_generic_to_shared(KV + ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8);
+  const uint32_t v_addr0 = (uint32_t)__cvta_generic_to_shared(KV + FA_BK * LDS + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+  const uint32_t kv_base = (uint32_t)__cvta_generic_to_shared(KV);
 
   float mxr[PE ? NG : 1][4];               // PE: x-marginal of P for rows g, g+8 at key columns 8*ng + 2t, +1
 #pragma unroll
@@ -72,21 +78,32 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   const int kstep = PE ? p.pe_w : FA_BK;    // keys per tile
   int tile_i = 0;
 
+  // asynchronous K/V tile fetch into stage `st` (rows beyond the tile are zero-filled)
+  auto fetch = [&](int k0, int st) {
+    const int kend = PE ? k0 + kstep : p.N;
+    for (int e = tid; e < FA_BK * CH; e += FA_THREADS) {
+      const int r = e / CH, c = (e % CH) * 8;
+      const bool ok = k0 + r < kend;
+      const __half* src = base + ((long long)s_kv * p.N + (ok ? k0 + r : 0)) * p.qkv_ld + head * D + c;
+      const uint32_t dk = kv_base + (uint32_t)(st * STAGE + r * LDS + c) * 2;
+      cp_async16(dk, src + p.C, ok);
+      cp_async16(dk + FA_BK * LDS * 2, src + 2 * p.C, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0, 0);
+
   for (int k0 = 0; k0 < p.N; k0 += kstep, ++tile_i) {
     const int kend = PE ? k0 + kstep : p.N;  // first key NOT in this tile
-    __syncthreads();
-    for (int e = tid; e < FA_BK * CH; e += FA_THREADS) {
-      int r = e / CH, c = (e % CH) * 8;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-      if (k0 + r < kend) {
-        const __half* src = base + ((long long)s_kv * p.N + k0 + r) * p.qkv_ld + head * D + c;
-        kv = *(const uint4*)(src + p.C);
-        vv = *(const uint4*)(src + 2 * p.C);
-      }
-      *(uint4*)(Ks + r * LDS + c) = kv;
-      *(uint4*)(Vs + r * LDS + c) = vv;
+    const int st = tile_i & 1;
+    if (k0 + kstep < p.N) {
+      fetch(k0 + kstep, st ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t k_addr = k_addr0 + st * STAGE * 2, v_addr = v_addr0 + st * STAGE * 2;
 
     // ---- S = Q K^T (16 x 64 per warp)
     float sc[NG][4];
@@ -166,6 +183,7 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
         mma16816(o[og + 1], a0, a1, a2, a3, b2, b3);
       }
     }
+    __syncthreads();   // every warp is done with this stage before it is refilled
   }
   // ---- finalise: quad-reduce the row sums, normalise, store fp16
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -225,16 +243,17 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
 
 template <int D, bool PE>
 static int launch_fa(const AttnP& p, cudaStream_t s) {
-  const size_t smem = (size_t)(FA_BQ + 2 * FA_BK) * (D + 8) * sizeof(__half) +
+  constexpr int FA_BK = (D > 128) ? 32 : 64;   // keeps two CTAs per SM at d = 256
+  const size_t smem = (size_t)(FA_BQ + 4 * FA_BK) * (D + 8) * sizeof(__half) +
                       (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
   S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attention_mma_kernel<D, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(attention_mma_kernel<D, FA_BK, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
   dim3 grid(cdiv(p.N, FA_BQ), p.heads, p.S);
-  attention_mma_kernel<D, PE><<<grid, FA_THREADS, smem, s>>>(p);
+  attention_mma_kernel<D, FA_BK, PE><<<grid, FA_THREADS, smem, s>>>(p);
   S2M2_LAUNCH_OK("attention_mma");
   return 0;
 }
@@ -242,7 +261,7 @@ static int launch_fa(const AttnP& p, cudaStream_t s) {
 int attention_mma_supported(const AttnP& p) {
   if (!p.qh || !p.oh) return 0;
   if (p.pesum) {  // PE variant: fp16 pesum, image rows as key tiles, head dims used at 1/32 resolution
-    if (!p.ph_half || p.pe_w > FA_BK || p.pe_h * p.pe_w != p.N || p.pe_h > 128) return 0;
+    if (!p.ph_half || p.pe_w > 64 || p.pe_h * p.pe_w != p.N || p.pe_h > 128) return 0;
     if (!(p.d == 16 || p.d == 32 || p.d == 64 || p.d == 96)) return 0;
   }
   if (p.qkv_ld % 8 || p.out_ld % 2 || !aligned(p.qkv, 16) || !aligned(p.out, 4)) return 0;

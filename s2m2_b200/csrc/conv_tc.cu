@@ -430,33 +430,46 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       constexpr int NCH = CG / 16;                       // 16-column chunks per warp
       uint4 rpre[NCH][2];
       const bool has_res = p.res != nullptr && !p.shuffle;
-      if (has_res && valid && p.rh) {
+      if (has_res && p.rh) {
+        // full-sector reads, same lane-pair trick as the stores: instruction 1 reads the even row of the pair (low half by
+        // the even lane, high half by the odd lane), instruction 2 the odd row; one exchange puts the halves back in place.
+        const bool odd = lane & 1;
+        const bool pv = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+        const long long popix = __shfl_xor_sync(0xffffffffu, opix, 1);
+        const long long row_e = odd ? popix : opix, row_o = odd ? opix : popix;   // even / odd row of the pair
+        const bool ve = odd ? pv : valid, vo = odd ? valid : pv;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int n = n0 + half * CG + c * 16;
+          uint4 a = make_uint4(0, 0, 0, 0), b = a;
           if (n < p.Cout) {
-            const uint4* rp = (const uint4*)((const __half*)p.res + opix * p.res_ld + n);
-            rpre[c][0] = __ldg(rp);
-            rpre[c][1] = __ldg(rp + 1);
+            const __half* rb = (const __half*)p.res + n + (odd ? 8 : 0);
+            if (ve) a = __ldg((const uint4*)(rb + row_e * p.res_ld));
+            if (vo) b = __ldg((const uint4*)(rb + row_o * p.res_ld));
           }
+          // even lane holds (own.lo, partner.lo), odd lane holds (partner.hi, own.hi): swap the foreign halves
+          const uint4 send = odd ? a : b;
+          uint4 recv;
+          recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+          recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+          rpre[c][0] = odd ? recv : a;     // own low half
+          rpre[c][1] = odd ? b : recv;     // own high half
         }
       }
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      // TMEM loads are double-buffered: chunk c+1 is in flight while chunk c goes through bias/activation/store
-      uint32_t rbuf[2][16];
       if (p.dbg & 2) valid = false;
-      if (n0 + half * CG < p.Cout) tmem_ld16(trow + half * CG, rbuf[0]);
+      // neighbour-lane exchange for full-sector stores (see below): lane l pairs with lane l^1
+      const bool pvalid = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int c0 = half * CG + c * 16;
         const int n = n0 + c0;
         if (n >= p.Cout) break;
+        uint32_t rr[16];
+        tmem_ld16(trow + c0, rr);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c + 1 < NCH && n + 16 < p.Cout) tmem_ld16(trow + c0 + 16, rbuf[(c + 1) & 1]);
-        const uint32_t* rr = rbuf[c & 1];
-        if (!valid) continue;
         float v[16];
         if (p.bias) {
 #pragma unroll
@@ -480,7 +493,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           off = pix * p.y_ld + co;
         } else {
           off = opix * p.y_ld + n;
-          if (has_res) {
+          if (has_res && valid) {
             if (p.rh) {
               const __half2* hr = (const __half2*)&rpre[c][0];
 #pragma unroll
@@ -501,13 +514,25 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         if (p.dbg & 1) {
           if (v[0] == 123.456f) ((float*)p.y)[0] = v[1];   // keep the math alive without storing
         } else if (p.yh) {
+          // fp16: a thread's 16 columns are one 32-byte sector = two 16-byte halves.  Writing them as two scattered
+          // 16-byte stores makes every store a partial-sector write; instead lanes l and l^1 swap one half so that
+          // each store instruction writes both halves of a sector from adjacent lanes (full 32 B sectors).
           __half2 h[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-          uint4* dst = (uint4*)((__half*)p.y + off);
-          dst[0] = *(uint4*)&h[0];
-          dst[1] = *(uint4*)&h[4];
-        } else {
+          const uint4 lo = *(uint4*)&h[0], hi = *(uint4*)&h[4];
+          const bool odd = lane & 1;
+          const uint4 send = odd ? lo : hi;
+          uint4 recv;
+          recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+          recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+          const long long poff = __shfl_xor_sync(0xffffffffu, off, 1);     // partner row's element offset
+          __half* yb = (__half*)p.y;
+          // store 1 -> even row of the pair: even lane writes its own low half, odd lane the even row's high half
+          if (odd ? pvalid : valid) *(uint4*)(yb + (odd ? poff + 8 : off)) = odd ? recv : lo;
+          // store 2 -> odd row of the pair: even lane writes the odd row's low half, odd lane its own high half
+          if (odd ? valid : pvalid) *(uint4*)(yb + (odd ? off + 8 : poff)) = odd ? hi : recv;
+        } else if (valid) {
           float4* dst = (float4*)((float*)p.y + off);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
