@@ -35,6 +35,7 @@ struct TcP {
   int KW, ph, pw, taps, stride;
   int cpb1, cpb2;        // 64-channel chunks per tap from x and x2
   int act, shuffle, Cr;
+  int tma_store;         // epilogue stages the tile in shared memory and writes it with cp.async.bulk.tensor (fp16, no scatter)
   int dbg;               // S2M2_TC_DBG experiments: 1 = no global stores, 2 = epilogue only drains (no math / stores)
 };
 
@@ -75,6 +76,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -104,6 +110,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
 struct TcMaps {
   CUtensorMap act[4];
   CUtensorMap w;
+  CUtensorMap out;   // v2 epilogue: box {BN/4 channels, 32 pixels of the tile} for the TMA store
 };
 
 template <int BN, int STAGES>
@@ -307,7 +314,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = (uint64_t*)(sB + STAGES * B_BYTES);  // full[S], empty[S], tfull[2], tempty[2]
+  constexpr uint32_t STG_BYTES = 32 * (BN / TC2_EPI_GROUPS) * 2;          // per epilogue warp: 32 rows x CG fp16
+  uint8_t* sStage = sB + STAGES * B_BYTES;                                  // 16 warps x STG_BYTES, 1024-aligned
+  uint64_t* bars = (uint64_t*)(sStage + 4 * TC2_EPI_GROUPS * 1024 * ((STG_BYTES + 1023) / 1024));  // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -409,6 +418,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
     const int half = (warp - 2) >> 2;
     constexpr int CG = BN / TC2_EPI_GROUPS;   // columns per group
     const int r = q * 32 + lane;
+    // TMA-store staging: this warp's 32 rows x CG columns, rows of CG*2 bytes, swizzled like the store tensor map
+    constexpr uint32_t STG_STRIDE = 1024 * ((32 * CG * 2 + 1023) / 1024);
+    constexpr uint32_t SWZ_MASK = (CG * 2 >= 128) ? 7u : ((CG * 2 == 64) ? 3u : 1u);
+    uint8_t* stg = sStage + (warp - 2) * STG_STRIDE;
+    const uint32_t stg_u32 = smem_u32(stg);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       int n0, img, x0, y0;
@@ -455,6 +469,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           rpre[c][0] = odd ? recv : a;     // own low half
           rpre[c][1] = odd ? b : recv;     // own high half
         }
+      }
+      if (p.tma_store) {   // the previous tile's bulk store must have read the staging tile before it is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
       }
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -513,6 +531,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         }
         if (p.dbg & 1) {
           if (v[0] == 123.456f) ((float*)p.y)[0] = v[1];   // keep the math alive without storing
+        } else if (p.tma_store) {
+          // stage this thread's 16 columns (two 16-byte units of its row) in the swizzled staging tile
+          __half2 h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t lin = (uint32_t)lane * (CG * 2) + (uint32_t)(c * 2 + u) * 16;
+            *(uint4*)(stg + (lin ^ (((lin >> 7) & SWZ_MASK) << 4))) = *(uint4*)&h[4 * u];
+          }
         } else if (p.yh) {
           // fp16: a thread's 16 columns are one 32-byte sector = two 16-byte halves.  Writing them as two scattered
           // 16-byte stores makes every store a partial-sector write; instead lanes l and l^1 swap one half so that
@@ -540,9 +568,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       }
       // all of this warp's TMEM reads have completed (wait::ld above): hand the accumulator back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (p.tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+        if (p.tma_store && n0 + half * CG < p.Cout && !(p.dbg & 3)) {
+          // one bulk tensor store: 32 pixels (rows q*32.. of the tile) x CG channels; TMA clips everything outside the tensor
+          const int r0 = q * 32;
+          int cx, cy;
+          if (p.flat) { cx = x0 + r0; cy = 0; }
+          else { cx = x0 + r0 % p.tw; cy = y0 + r0 / p.tw; }
+          tma_store_4d(&maps.out, stg_u32, n0 + half * CG, cx, cy, img);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -650,7 +691,9 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
 
 template <int BN, int STAGES>
 static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles, cudaStream_t s) {
-  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr size_t stg = 4 * TC2_EPI_GROUPS * 1024 * ((32 * (BN / TC2_EPI_GROUPS) * 2 + 1023) / 1024);
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + stg + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
@@ -729,8 +772,30 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   p.dbg = dbg;
   if (!use_v1) {
     const int nt = cdiv(a->Cout, BN);
-    if (BN == 256) return launch_tc2<256, 4>(maps, p, (int)mtiles, nt, s);
-    if (BN == 128) return launch_tc2<128, 6>(maps, p, (int)mtiles, nt, s);
+    // output tensor map for the TMA-store epilogue: box = {BN/4 channels, the 32 pixels one epilogue warp owns}
+    static const int no_tma_store = getenv("S2M2_TC_NO_TMA_STORE") ? atoi(getenv("S2M2_TC_NO_TMA_STORE")) : 0;
+    p.tma_store = (!no_tma_store && y.dtype == S2M2_F16 && !a->shuffle2x2) ? 1 : 0;
+    if (p.tma_store) {
+      const int CG = BN / TC2_EPI_GROUPS;
+      cuuint64_t dims[4], strides[3];
+      cuuint32_t box[4] = {(cuuint32_t)CG, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+      if (p.flat) {
+        dims[0] = y.C; dims[1] = (cuuint64_t)y.N * y.H * y.W; dims[2] = 1; dims[3] = 1;
+        strides[0] = (cuuint64_t)y.ld * 2; strides[1] = strides[0] * dims[1]; strides[2] = strides[1];
+      } else {
+        dims[0] = y.C; dims[1] = y.W; dims[2] = y.H; dims[3] = y.N;
+        strides[0] = (cuuint64_t)y.ld * 2; strides[1] = strides[0] * y.W; strides[2] = strides[1] * y.H;
+        if (p.tw < 32) { box[1] = p.tw; box[2] = 32 / p.tw; }
+      }
+      const CUtensorMapSwizzle sw = CG * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (CG * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      CUresult r = get_encode()(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+    } else {
+      maps.out = maps.w;
+    }
+    if (BN == 256) return launch_tc2<256, 3>(maps, p, (int)mtiles, nt, s);
+    if (BN == 128) return launch_tc2<128, 5>(maps, p, (int)mtiles, nt, s);
     return launch_tc2<64, 8>(maps, p, (int)mtiles, nt, s);
   }
   dim3 grid((unsigned)mtiles, cdiv(a->Cout, BN));
