@@ -76,10 +76,14 @@ int s2m2b200_conv2d(const S2m2Conv* a, void* stream);
  * If pesum.ptr != NULL the contextual relative positional term of attentions.py:46-47 is produced:
  *   pesum[s,t,h,0:16]  = sum_j P[t,j] * 0.5*pe_x[x_t - x_j + pw - 1]
  *   pesum[s,t,h,16:32] = sum_j P[t,j] * 0.5*pe_y[y_t - y_j + ph - 1],  token t = y*pw + x
- * (the (N,N,32) tensor of utils.py:32-60 is never materialised). */
+ * (the (N,N,32) tensor of utils.py:32-60 is never materialised).
+ * work / work_bytes: optional scratch (s2m2b200_attention_workspace_bytes) that enables the tcgen05 whole-row kernel
+ * for the scan-line blocks (it holds V^T); NULL / 0 selects the mma.sync / CUDA-core kernels. */
 int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, int32_t N, int32_t heads,
                        int32_t kv_shift, const float* pe_x, const float* pe_y, int32_t ph, int32_t pw,
-                       const S2m2Tensor* pesum, void* stream);
+                       const S2m2Tensor* pesum, void* work, int64_t work_bytes, void* stream);
+/* Scratch bytes the tcgen05 attention kernel needs for (S sequences, N tokens, heads, head dim d); 0 = not applicable. */
+int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, int32_t d, int32_t dtype);
 
 /* Relative-PE table of utils.py:32-60 for one axis of length n: HOST output (2n+1, 16) floats. */
 int s2m2b200_pe_table(int32_t n, float* host_out);

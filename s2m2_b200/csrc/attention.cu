@@ -190,9 +190,19 @@ int attention_simt_launch(const AttnP& p, cudaStream_t s) {
 
 using namespace s2m2;
 
+extern "C" int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, int32_t d, int32_t dtype) {
+  AttnP p{};
+  p.S = S; p.N = N; p.heads = heads; p.d = d; p.C = heads * d; p.qh = p.oh = (dtype == S2M2_F16);
+  static int dummy_aligned[4];
+  p.qkv = dummy_aligned; p.out = dummy_aligned;   // alignment checks are on the real pointers at launch time
+  p.qkv_ld = 3 * p.C; p.out_ld = p.C;
+  if (!p.qh || !(d == 64 || d == 128 || d == 256) || N < 48 || N > 384) return 0;
+  return (int64_t)attention_tc_workspace_bytes(p);
+}
+
 extern "C" int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, int32_t N, int32_t heads,
                                   int32_t kv_shift, const float* pe_x, const float* pe_y, int32_t ph, int32_t pw,
-                                  const S2m2Tensor* pesum, void* stream) {
+                                  const S2m2Tensor* pesum, void* work, int64_t work_bytes, void* stream) {
   const int C = out->C;
   S2M2_CHECK(qkv->C == 3 * C && C % heads == 0, "attention: qkv must have 3*C channels, C %% heads == 0");
   S2M2_CHECK(npix(*qkv) == (long long)S * N && npix(*out) == (long long)S * N, "attention: S*N != number of tokens");
@@ -210,7 +220,10 @@ extern "C" int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, 
   if (p.d % 4 == 0) {
     S2M2_CHECK(qkv->ld % 4 == 0 && aligned(qkv->ptr, 4 * esize(qkv->dtype)), "attention: qkv view must be 4-element aligned");
   }
-  static const int force_simt = getenv("S2M2_ATTN_IMPL") ? atoi(getenv("S2M2_ATTN_IMPL")) == 1 : 0;
+  static const int impl = getenv("S2M2_ATTN_IMPL") ? atoi(getenv("S2M2_ATTN_IMPL")) : 0;   // 1 = CUDA-core, 2 = mma.sync, 0 = auto
+  const bool force_simt = impl == 1;
+  if (impl == 0 && work && attention_tc_supported(p) && work_bytes >= (int64_t)attention_tc_workspace_bytes(p))
+    return attention_tc_launch(p, work, (cudaStream_t)stream);
   if (!force_simt && attention_mma_supported(p)) return attention_mma_launch(p, (cudaStream_t)stream);
   return attention_simt_launch(p, (cudaStream_t)stream);
 }

@@ -15,4 +15,7 @@ struct AttnP {
 int attention_simt_launch(const AttnP& p, cudaStream_t s);
 int attention_mma_supported(const AttnP& p);
 int attention_mma_launch(const AttnP& p, cudaStream_t s);
+int attention_tc_supported(const AttnP& p);
+size_t attention_tc_workspace_bytes(const AttnP& p);
+int attention_tc_launch(const AttnP& p, void* workspace, cudaStream_t s);
 }  // namespace s2m2

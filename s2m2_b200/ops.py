@@ -46,12 +46,13 @@ def load_library():
     lib.s2m2b200_last_error.restype = C.c_char_p
     lib.s2m2b200_version.restype = C.c_char_p
     lib.s2m2b200_launch_count.restype = C.c_int64
+    lib.s2m2b200_attention_workspace_bytes.restype = C.c_int64
     _lib = lib
     return lib
 
 
 EXPORTS = [
-    "s2m2b200_conv2d", "s2m2b200_attention", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
+    "s2m2b200_conv2d", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
@@ -86,6 +87,7 @@ class CudaOps:
         if conv_impl is None:
             conv_impl = int(os.environ.get("S2M2_CONV_IMPL", "0"))
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
+        self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
         self._pe = {}
         self._gn_work = {}
 
@@ -161,14 +163,20 @@ class CudaOps:
     def attention(self, qkv, o, S, N, heads, kv_shift, pe=None, pesum=None):
         q = tview(qkv)
         ot = tview(o)
+        work, wbytes = None, 0
+        if pesum is None and self.attn_tc:
+            wbytes = int(self.lib.s2m2b200_attention_workspace_bytes(S, N, heads, o.shape[3] // heads, _DT[qkv.dtype]))
+            if wbytes > 0:
+                wt = torch.empty(wbytes // 2, dtype=torch.float16, device=qkv.device)   # V^T scratch of the tcgen05 kernel
+                work = C.c_void_p(wt.data_ptr())
         if pesum is not None:
             px, py, ph, pw = pe
             ps = S2m2Tensor(pesum.data_ptr(), _DT[pesum.dtype], 1, 1, S * N * heads, 32, 32)
             rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, C.c_void_p(px.data_ptr()),
-                                             C.c_void_p(py.data_ptr()), ph, pw, C.byref(ps), self._stream())
+                                             C.c_void_p(py.data_ptr()), ph, pw, C.byref(ps), None, C.c_int64(0), self._stream())
         else:
             rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, None, None, 0, 0, None,
-                                             self._stream())
+                                             work, C.c_int64(wbytes), self._stream())
         self._chk(rc, "attention")
 
     # -- norms / resampling / element-wise

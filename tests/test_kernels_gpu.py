@@ -133,6 +133,13 @@ ATTN_CASES = [
     (2, 100, 8, 4, False, None),
     (3, 70, 1, 256, False, None),
     (2, 50, 2, 96, True, None),
+    (16, 304, 1, 256, True, None),      # L level-0 scan-line cross attention (tcgen05 whole-row kernel)
+    (6, 304, 1, 256, False, None),
+    (8, 152, 2, 128, True, None),       # L level 1
+    (8, 76, 4, 128, False, None),       # L level 2
+    (8, 160, 1, 128, True, None),       # S level 0
+    (4, 80, 2, 64, False, None),        # S level 1
+    (2, 384, 1, 64, False, None),       # longest row the whole-row kernel takes
 ]
 
 
