@@ -5,8 +5,9 @@
 //     phase 1  S[128 x N]   = Q K^T      tcgen05.mma (M=128, N=64 per key block, K=d), S in TMEM columns [0, N_pad)
 //     phase 2  P = softmax(S)             4 warps, thread = row: TMEM -> registers -> fp16 P written to shared memory in the
 //                                         K-major 128B-swizzled layout the tensor core reads as the A operand
-//     phase 3  O[128 x d]   = P V         tcgen05.mma (M=128, N=d, K=64 per key block); V comes pre-transposed (V^T: d x N_pad,
-//                                         keys contiguous) so that every operand is K-major; O re-uses S's TMEM columns
+//     phase 3  O[128 x d]   = P V         tcgen05.mma (M=128, N=d, K=64 per key block); V is consumed as it lies in memory
+//                                         ([key][channel] = MN-major B operand, b_major = 1): no transpose pass; O re-uses S's
+//                                         TMEM columns
 //     phase 4  out = O / rowsum           TMEM -> registers -> global (full-sector stores)
 //   warp 0 = TMA producer (Q once, then K blocks, then V^T blocks through one smem ring), warp 1 = MMA issuer + TMEM
 //   allocator, warps 2..5 = softmax / epilogue.
@@ -30,7 +31,6 @@ struct AtcP {
 struct AtcMaps {
   CUtensorMap q;   // qkv (tokens x 3C): box {64 ch, 128 tokens}
   CUtensorMap k;   // qkv (tokens x 3C): box {64 ch, 64 tokens}
-  CUtensorMap vt;  // V^T (S*heads*d rows x N_pad keys): box {64 keys, d rows}
 };
 
 // ---- PTX wrappers (same idioms as conv_tc.cu) ---------------------------------------------------
@@ -89,6 +89,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {  // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major, SWIZZLE_128B: rows = K (keys) of 128 B = 64 MN elements; 8-row atoms SBO = 1024 B apart along K; the next
+// 64-element MN chunk lies LBO = 8192 B further (one [64 keys][128 B] TMA box).  (cute: Layout_MN_SW128_Atom)
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 }  // namespace atc
 using namespace atc;
 
@@ -96,7 +101,7 @@ template <int D>
 __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __grid_constant__ AtcMaps maps, const AtcP p) {
   constexpr int KC = D / 64;                       // 64-channel chunks of the head dim
   constexpr uint32_t Q_BYTES = 128 * D * 2;        // KC chunks of [128 rows][128 B]
-  constexpr uint32_t BLK_BYTES = 64 * D * 2;       // one ring slot: K block (KC x [64][128 B]) or V^T block ([D][128 B])
+  constexpr uint32_t BLK_BYTES = 64 * D * 2;       // one ring slot: K block or V block, both KC x [64 keys][128 B]
   constexpr int NST = (D >= 256) ? 3 : 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -148,7 +153,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
           for (int kc = 0; kc < KC; ++kc)
             tma_load_2d(&maps.k, dst + kc * 8192, full0 + 8 * st, p.C + head * D + kc * 64, s_kv * p.N + it * 64);
         } else {
-          tma_load_2d(&maps.vt, dst, full0 + 8 * st, (it - NKB) * 64, (s_kv * p.heads + head) * D);
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_2d(&maps.k, dst + kc * 8192, full0 + 8 * st, 2 * p.C + head * D + kc * 64, s_kv * p.N + (it - NKB) * 64);
         }
       }
     }
@@ -156,7 +163,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_o = (1u << 4) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // O = P V: B = V block as loaded, [64 keys][64 ch] x KC chunks = MN-major (channels contiguous): b_major bit 16
+      const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(qfull, 0);
       for (int it = 0; it < NKB; ++it) {            // S[:, 64*it ..] = Q K_blk^T
         const int st = it % NST;
@@ -177,9 +185,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
         const int it = NKB + b, st = it % NST;
         mbar_wait(full0 + 8 * st, (it / NST) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t ad = make_sdesc(smem_u32(sQP + b * 16384)), bd = make_sdesc(smem_u32(sRing + st * BLK_BYTES));
+        const uint64_t ad = make_sdesc(smem_u32(sQP + b * 16384)), bd = make_sdesc_mn(smem_u32(sRing + st * BLK_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc_o, (b | k) != 0);
+        for (int k = 0; k < 4; ++k)   // A: +32 B per 16 keys within the 128 B row; B: +16 key rows = 2 swizzle atoms = 2048 B
+          umma_f16(tmem_base, ad + 2 * k, bd + (2048 >> 4) * k, idesc_o, (b | k) != 0);
         umma_commit(empty0 + 8 * st);
       }
       umma_commit(ofull);
@@ -262,24 +271,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   }
 }
 
-// V (tokens x C slice of qkv) -> V^T per (sequence, head): vt[(s*heads + h)*d + c][j], j < N_pad (zero padded)
-__global__ void vt_transpose_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ vt, int N, int N_pad,
-                                    int heads, int d, int C) {
-  __shared__ __half tile[32][34];
-  const int sh = blockIdx.z, s = sh / heads, h = sh - s * heads;
-  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int j = j0 + i;
-    tile[i][tx] = (j < N) ? qkv[((long long)s * N + j) * ld + 2 * C + h * d + c0 + tx] : __float2half(0.f);
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i;
-    vt[((long long)sh * d + c) * N_pad + j0 + tx] = tile[tx][i];
-  }
-}
-
 // ---- host ----------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 atc_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -309,10 +300,7 @@ int attention_tc_supported(const AttnP& p) {
   return ok;
 }
 
-size_t attention_tc_workspace_bytes(const AttnP& p) {
-  const int N_pad = (p.N + 63) / 64 * 64;
-  return (size_t)p.S * p.heads * p.d * N_pad * sizeof(__half);
-}
+size_t attention_tc_workspace_bytes(const AttnP& p) { (void)p; return 16; }   // no scratch needed any more (kept for the ABI)
 
 template <int D>
 static int launch_atc(const AtcMaps& maps, const AtcP& p, dim3 grid, size_t smem, cudaStream_t s) {
@@ -335,12 +323,7 @@ int attention_tc_launch(const AttnP& a, void* workspace, cudaStream_t s) {
   const int need = p.N_pad > D ? p.N_pad : D;
   p.tmem_cols = need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
   p.sl2 = a.scale * 1.4426950408889634f;
-  __half* vt = (__half*)workspace;
-  {
-    dim3 g(p.N_pad / 32, D / 32, a.S * a.heads);
-    vt_transpose_kernel<<<g, 256, 0, s>>>((const __half*)a.qkv, a.qkv_ld, vt, a.N, p.N_pad, a.heads, D, a.C);
-    S2M2_LAUNCH_OK("vt_transpose");
-  }
+  (void)workspace;
   AtcMaps maps;
   const long long tokens = (long long)a.S * a.N;
   {
@@ -354,11 +337,6 @@ int attention_tc_launch(const AttnP& a, void* workspace, cudaStream_t s) {
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     S2M2_CHECK(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "attention_tc: cuTensorMapEncodeTiled(qkv) failed: %d %d", (int)r1, (int)r2);
-    cuuint64_t vdims[2] = {(cuuint64_t)p.N_pad, (cuuint64_t)a.S * a.heads * D}, vstr[1] = {(cuuint64_t)p.N_pad * 2};
-    cuuint32_t boxv[2] = {64, (cuuint32_t)D};
-    CUresult r3 = atc_encode()(&maps.vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, vdims, vstr, boxv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    S2M2_CHECK(r3 == CUDA_SUCCESS, "attention_tc: cuTensorMapEncodeTiled(vt) failed: %d", (int)r3);
   }
   const int NST = D >= 256 ? 3 : 4;
   const size_t r0 = (size_t)128 * 2 * (p.N_pad > D ? p.N_pad : D);

@@ -257,6 +257,69 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) conv_simt_kernel(Con
   }
 }
 
+// ---- tiny-K layers (K = KH*KW*Cin <= 32: 1->C, 2->C, 9->C encoders of the refiner) -------------------------------
+// The tiled GEMM above wastes its K loop on them; here a thread gathers its pixel's K inputs once and produces 8
+// output channels from weights held in shared memory; 8-channel groups of one pixel are adjacent threads (coalesced).
+constexpr int SMALLK_MAX = 32;
+__global__ void __launch_bounds__(256) conv_smallk_kernel(ConvP p) {
+  extern __shared__ float sw[];                  // [Cout][K] weights then [Cout] bias
+  float* sb = sw + p.Cout * p.K;
+  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[i] = ld1(p.w, i, p.wh);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
+  const int groups = (p.Cout + 7) / 8;
+  const long long total = (long long)p.M * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / groups), g = (int)(i - (long long)m * groups);
+    const int ox = m % p.Wo;
+    const int t = m / p.Wo;
+    const int oy = t % p.Ho, n = t / p.Ho;
+    float a[SMALLK_MAX];
+#pragma unroll
+    for (int k = 0; k < SMALLK_MAX; ++k) {
+      float v = 0.f;
+      if (k < p.K) {
+        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        const int iy = oy * p.stride - p.ph + ky, ix = ox * p.stride - p.pw + kx;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = ld1(p.x, (((long long)n * p.H + iy) * p.W + ix) * p.x_ld + ci, p.xh);
+      }
+      a[k] = v;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      float acc = 0.f;
+      if (co < p.Cout) {
+        acc = sb[co];
+        const float* wr = sw + co * p.K;
+#pragma unroll
+        for (int k = 0; k < SMALLK_MAX; ++k)
+          if (k < p.K) acc = fmaf(a[k], wr[k], acc);
+        acc = act_apply(acc, p.act);
+      }
+      o[j] = acc;
+    }
+    const long long off = (long long)m * p.y_ld + g * 8;
+    if (p.vout && g * 8 + 8 <= p.Cout && (p.y_ld % 8 == 0)) {
+      if (p.yh) {
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+        *(uint4*)((__half*)p.y + off) = *(uint4*)h;
+      } else {
+        *(float4*)((float*)p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
+        *(float4*)((float*)p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (g * 8 + j < p.Cout) st1(p.y, off + j, p.yh, o[j]);
+    }
+  }
+}
+
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_cfg(const ConvP& p, int batch, bool vec, cudaStream_t s) {
   dim3 grid(cdiv(p.M, BM), cdiv(p.Cout, BN), batch);
@@ -290,6 +353,15 @@ int conv_simt_launch(const S2m2Conv* a, cudaStream_t s) {
   bool out_al = aligned(y.ptr, 4 * esize(y.dtype)) && (p.y_bs % 4 == 0) && (!res.ptr || aligned(res.ptr, 4 * esize(res.dtype)));
   p.vout = out_al && p.y_ld % 4 == 0 &&
            (p.shuffle ? p.Cr % 4 == 0 : (p.Cout % 4 == 0 && (!res.ptr || res.ld % 4 == 0)));
+  if (p.K <= SMALLK_MAX && p.Cout >= 16 && p.Cout <= 256 && batch == 1 && !p.x2 && !p.res && !p.shuffle) {
+    const long long total = (long long)p.M * ((p.Cout + 7) / 8);
+    long long g = (total + 255) / 256;
+    if (g > 148LL * 32) g = 148LL * 32;
+    const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout);
+    conv_smallk_kernel<<<(int)g, 256, smem, s>>>(p);
+    S2M2_LAUNCH_OK("conv_smallk");
+    return 0;
+  }
   if (p.Cout > 64) return launch_cfg<128, 128, 16, 8, 8>(p, batch, vec, s);
   if (p.Cout > 32) return launch_cfg<128, 64, 16, 8, 4>(p, batch, vec, s);
   if (p.Cout > 16) return launch_cfg<128, 32, 16, 4, 4>(p, batch, vec, s);

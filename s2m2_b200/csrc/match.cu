@@ -10,7 +10,7 @@ namespace s2m2 {
 // streamed from L2 once per half-iteration (2*iters + 1 passes); u, v live in shared memory.
 //   A(i,j) = cv[i,j] (or -1e4 where j > i when use_positivity), dust-bin row/column = 0.
 // ------------------------------------------------------------------------------------------------
-constexpr int SK_THREADS = 256;
+constexpr int SK_THREADS = 512;   // 2 CTAs/SM x 148 SMs >= the 256 scan-lines of L@1216x1024: one wave
 constexpr int SK_WARPS = SK_THREADS / 32;
 
 __device__ __forceinline__ float sk_a(const float* __restrict__ row_i, int i, int j, int w, int pos) {
