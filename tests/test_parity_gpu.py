@@ -168,6 +168,48 @@ def test_l_1216x1024_headline_config_vs_oracle_on_gpu():
         torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("model_type,H,W", [("M", 256, 384), ("XL", 256, 320)])
+def test_other_model_sizes_vs_oracle(model_type, H, W):
+    """M (CH192/NTR2) and XL (CH384/NTR3): head dims 192/96/48 and 384/192/96 — the non-power-of-two paths."""
+    from s2m2_b200.weights import MODEL_TABLE
+    C, NTR = MODEL_TABLE[model_type]
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, H, W, 1)
+    ot = {}
+    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3, ot)]
+    am_ref = ot["disp_init.argmax"].cpu()
+    del ot
+    for prec, tol in (("fp32", 1e-3), ("fp16", 5e-3)):
+        m = _model(C, NTR, sd, precision=prec)
+        m.taps = {}
+        out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+        flips = int((m.taps["disp_init.argmax"].cpu() != am_ref).sum())
+        err = (out[0] - ref[0]).abs()
+        print(f"{model_type} {W}x{H} {prec}: EPE {err.mean().item():.3e} max {err.max().item():.3e} argmax flips {flips}/{am_ref.numel()}")
+        assert err.mean().item() < tol
+        if prec == "fp32":
+            assert flips == 0
+        del m
+        torch.cuda.empty_cache()
+
+
+def test_xl_2432x2048_config_runs_and_matches_oracle():
+    """BASELINE config 4 (XL, 2432x2048: the 757 MB cost volume / N=4864 global attention case)."""
+    C, NTR = 384, 3
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, 2048, 2432, 1)
+    m = _model(C, NTR, sd, precision="fp16")
+    out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+    del m
+    torch.cuda.empty_cache()
+    assert all(torch.isfinite(t).all() for t in out)
+    assert out[0].shape == (1, 1, 2048, 2432)
+    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3)]
+    err = (out[0] - ref[0]).abs()
+    print(f"XL 2432x2048 fp16: EPE {err.mean().item():.3e} max {err.max().item():.3e} occ {(out[1] - ref[1]).abs().mean().item():.2e}")
+    assert err.mean().item() < 5e-3
+
+
 def test_batch_independence_and_determinism():
     """Pairs are independent units: a batch of two identical pairs gives two identical results,
     equal to the single-pair result, and repeated calls are bit-identical."""
