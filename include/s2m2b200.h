@@ -110,11 +110,12 @@ int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_
                         const S2m2Tensor* out, void* stream);
 
 /* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images -> (2B,H,W,16)
- * (s2m2.py:86-87, submodules.py:70-72,89).  w0 (16,3), w1 (16,16), biases (16), all fp32. */
+ * (s2m2.py:86-87, submodules.py:70-72,89).  w0 (16,3), w1 (16,16), biases (16): fp32 HOST pointers (they become kernel parameters). */
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream);
 /* Fused UpsampleMask1x inputs (submodules.py:121-124,138-139): out[...,0:16] = relu(convT3x3(up[...,0])),
- * out[...,16:32] = relu(convT3x3(rgb)); wd (16,9) / wr (16,27) are the equivalent flipped conv weights, tap-major. */
+ * out[...,16:32] = relu(convT3x3(rgb)); wd (16,9) / wr (16,27) are the equivalent flipped conv weights, tap-major;
+ * weights and biases are fp32 HOST pointers. */
 int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* wd, const float* bd, const float* wr,
                            const float* br, const S2m2Tensor* out, void* stream);
 

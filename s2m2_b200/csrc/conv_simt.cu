@@ -262,61 +262,37 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) conv_simt_kernel(Con
 // output channels from weights held in shared memory; 8-channel groups of one pixel are adjacent threads (coalesced).
 constexpr int SMALLK_MAX = 32;
 __global__ void __launch_bounds__(256) conv_smallk_kernel(ConvP p) {
-  extern __shared__ float sw[];                  // [Cout][K] weights then [Cout] bias
+  extern __shared__ float sw[];                  // [K][Cout] weights (transposed: lanes read consecutive channels) then [Cout] bias
   float* sb = sw + p.Cout * p.K;
-  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) sw[i] = ld1(p.w, i, p.wh);
+  for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) {
+    const int co = i / p.K, k = i - co * p.K;
+    sw[k * p.Cout + co] = ld1(p.w, i, p.wh);
+  }
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias ? p.bias[i] : 0.f;
   __syncthreads();
-  const int groups = (p.Cout + 7) / 8;
-  const long long total = (long long)p.M * groups;
+  const int NG = p.Cout >> 3;                    // threads per pixel; thread g owns channels g, g+NG, ..., g+7*NG
+  const long long total = (long long)p.M * NG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / groups), g = (int)(i - (long long)m * groups);
+    const int m = (int)(i / NG), g = (int)(i - (long long)m * NG);
     const int ox = m % p.Wo;
     const int t = m / p.Wo;
     const int oy = t % p.Ho, n = t / p.Ho;
-    float a[SMALLK_MAX];
-#pragma unroll
-    for (int k = 0; k < SMALLK_MAX; ++k) {
-      float v = 0.f;
-      if (k < p.K) {
-        const int tap = k / p.Cin, ci = k - tap * p.Cin;
-        const int ky = tap / p.KW, kx = tap - ky * p.KW;
-        const int iy = oy * p.stride - p.ph + ky, ix = ox * p.stride - p.pw + kx;
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = ld1(p.x, (((long long)n * p.H + iy) * p.W + ix) * p.x_ld + ci, p.xh);
-      }
-      a[k] = v;
-    }
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = g * 8 + j;
-      float acc = 0.f;
-      if (co < p.Cout) {
-        acc = sb[co];
-        const float* wr = sw + co * p.K;
+    for (int j = 0; j < 8; ++j) o[j] = sb[g + j * NG];
+    for (int k = 0; k < p.K; ++k) {
+      const int tap = k / p.Cin, ci = k - tap * p.Cin;
+      const int ky = tap / p.KW, kx = tap - ky * p.KW;
+      const int iy = oy * p.stride - p.ph + ky, ix = ox * p.stride - p.pw + kx;
+      float a = 0.f;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) a = ld1(p.x, (((long long)n * p.H + iy) * p.W + ix) * p.x_ld + ci, p.xh);
+      const float* wr = sw + k * p.Cout + g;
 #pragma unroll
-        for (int k = 0; k < SMALLK_MAX; ++k)
-          if (k < p.K) acc = fmaf(a[k], wr[k], acc);
-        acc = act_apply(acc, p.act);
-      }
-      o[j] = acc;
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(a, wr[j * NG], o[j]);
     }
-    const long long off = (long long)m * p.y_ld + g * 8;
-    if (p.vout && g * 8 + 8 <= p.Cout && (p.y_ld % 8 == 0)) {
-      if (p.yh) {
-        __half2 h[4];
+    const long long off = (long long)m * p.y_ld + g;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-        *(uint4*)((__half*)p.y + off) = *(uint4*)h;
-      } else {
-        *(float4*)((float*)p.y + off) = make_float4(o[0], o[1], o[2], o[3]);
-        *(float4*)((float*)p.y + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (g * 8 + j < p.Cout) st1(p.y, off + j, p.yh, o[j]);
-    }
+    for (int j = 0; j < 8; ++j) st1(p.y, off + j * NG, p.yh, act_apply(o[j], p.act));
   }
 }
 
@@ -353,8 +329,8 @@ int conv_simt_launch(const S2m2Conv* a, cudaStream_t s) {
   bool out_al = aligned(y.ptr, 4 * esize(y.dtype)) && (p.y_bs % 4 == 0) && (!res.ptr || aligned(res.ptr, 4 * esize(res.dtype)));
   p.vout = out_al && p.y_ld % 4 == 0 &&
            (p.shuffle ? p.Cr % 4 == 0 : (p.Cout % 4 == 0 && (!res.ptr || res.ld % 4 == 0)));
-  if (p.K <= SMALLK_MAX && p.Cout >= 16 && p.Cout <= 256 && batch == 1 && !p.x2 && !p.res && !p.shuffle) {
-    const long long total = (long long)p.M * ((p.Cout + 7) / 8);
+  if (p.K <= SMALLK_MAX && p.Cout >= 16 && p.Cout % 8 == 0 && p.Cout <= 256 && batch == 1 && !p.x2 && !p.res && !p.shuffle) {
+    const long long total = (long long)p.M * (p.Cout / 8);
     long long g = (total + 255) / 256;
     if (g > 148LL * 32) g = 148LL * 32;
     const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout);

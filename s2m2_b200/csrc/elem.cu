@@ -1,5 +1,7 @@
 // Bandwidth-bound kernels: norms, resampling, gates, layout conversion, refiner glue.  All NHWC, any pixel
 // stride, fp32 or fp16 storage (runtime flag), fp32 math.  Reference lines: see include/s2m2b200.h.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace s2m2 {
@@ -232,14 +234,10 @@ __global__ void preprocess_kernel(const float* __restrict__ left, const float* _
 // fused full-resolution tiny-channel layers (thread per pixel; weights in shared memory)
 // ------------------------------------------------------------------------------------------------
 // stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16)   (s2m2.py:86-87, submodules.py:70-72)
-__global__ void stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
-                            const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
-                            const float* __restrict__ b1, TV o) {
-  __shared__ float sw0[48], sb0[16], sw1[256], sb1[16];
-  for (int i = threadIdx.x; i < 48; i += blockDim.x) sw0[i] = w0[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sw1[i] = w1[i];
-  if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
-  __syncthreads();
+struct StemW { float w0[48], b0[16], w1[256], b1[16]; };      // passed by value: constant bank, warp-uniform reads
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
+                                                   const __grid_constant__ StemW wts, TV o) {
+  const float* sw0 = wts.w0; const float* sb0 = wts.b0; const float* sw1 = wts.w1; const float* sb1 = wts.b1;
   const long long HW = (long long)H * W, total = 2LL * B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long n = i / HW, hw = i - n * HW;
@@ -268,13 +266,10 @@ __global__ void stem_kernel(const float* __restrict__ left, const float* __restr
 
 // UpsampleMask1x inputs: relu(convT3x3(disp_up, 1->16)) | relu(convT3x3(rgb, 3->16))  (submodules.py:121-124,138-139)
 // weights are the equivalent (flipped) conv weights, tap-major: wd[co][tap], wr[co][tap*3 + ci]
-__global__ void mask1x_inputs_kernel(const float4* __restrict__ up, TV rgb, int B, int H, int W, const float* __restrict__ wd,
-                                     const float* __restrict__ bd, const float* __restrict__ wr, const float* __restrict__ br, TV o) {
-  __shared__ float swd[144], swr[432], sbd[16], sbr[16];
-  for (int i = threadIdx.x; i < 144; i += blockDim.x) swd[i] = wd[i];
-  for (int i = threadIdx.x; i < 432; i += blockDim.x) swr[i] = wr[i];
-  if (threadIdx.x < 16) { sbd[threadIdx.x] = bd[threadIdx.x]; sbr[threadIdx.x] = br[threadIdx.x]; }
-  __syncthreads();
+struct Mask1xW { float wd[144], wr[432], bd[16], br[16]; };
+__global__ void __launch_bounds__(256) mask1x_inputs_kernel(const float4* __restrict__ up, TV rgb, int B, int H, int W,
+                                                            const __grid_constant__ Mask1xW wts, TV o) {
+  const float* swd = wts.wd; const float* swr = wts.wr; const float* sbd = wts.bd; const float* sbr = wts.br;
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int X = (int)(i % W);
@@ -491,7 +486,9 @@ int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
   S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 16 && vec4_ok(*out), "stem: output must be (2B,H,W,16), 4-aligned");
-  stem_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, w0, b0, w1, b1, tv(*out));
+  StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
+  memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
+  stem_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, hw, tv(*out));
   S2M2_LAUNCH_OK("stem");
   return 0;
 }
@@ -500,8 +497,10 @@ int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* 
                            const float* br, const S2m2Tensor* out, void* stream) {
   S2M2_CHECK(rgb->C == 3 && out->C == 32 && npix(*rgb) == npix(*out) && vec4_ok(*out) && aligned(up, 16),
              "mask1x_inputs: rgb (B,H,W,3), out a 32-channel 4-aligned view, up 16-byte aligned");
+  Mask1xW hw;   // wd/bd/wr/br are HOST pointers (2.4 KB of weights as a kernel parameter)
+  memcpy(hw.wd, wd, sizeof(hw.wd)); memcpy(hw.bd, bd, sizeof(hw.bd)); memcpy(hw.wr, wr, sizeof(hw.wr)); memcpy(hw.br, br, sizeof(hw.br));
   mask1x_inputs_kernel<<<grid_for(npix(*out)), 256, 0, (cudaStream_t)stream>>>((const float4*)up, tv(*rgb), rgb->N, rgb->H, rgb->W,
-                                                                                  wd, bd, wr, br, tv(*out));
+                                                                                  hw, tv(*out));
   S2M2_LAUNCH_OK("mask1x_inputs");
   return 0;
 }

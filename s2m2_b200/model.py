@@ -243,8 +243,9 @@ class S2M2(nn.Module):
         P: Dict[str, object] = {}
         b = "cnn_backbone"
         f32c = lambda n: self._w(n).float().contiguous()
-        P["bb"] = {"w0": f32c(f"{b}.conv0.0.weight").reshape(16, 3).contiguous(), "b0": f32c(f"{b}.conv0.0.bias"),
-                   "w1": f32c(f"{b}.conv0.2.weight").reshape(16, 16).contiguous(), "b1": f32c(f"{b}.conv0.2.bias"),
+        hostc = lambda t: t.detach().float().cpu().contiguous()      # tiny weights that travel as kernel parameters
+        P["bb"] = {"w0": hostc(self._w(f"{b}.conv0.0.weight").reshape(16, 3)), "b0": hostc(self._w(f"{b}.conv0.0.bias")),
+                   "w1": hostc(self._w(f"{b}.conv0.2.weight").reshape(16, 16)), "b1": hostc(self._w(f"{b}.conv0.2.bias")),
                    "d0": self._conv(f"{b}.conv1_down.0", stride=2), "d2": self._conv(f"{b}.conv1_down.2"),
                    "gn_w": self._w(f"{b}.norm1.weight").float().contiguous(),
                    "gn_b": self._w(f"{b}.norm1.bias").float().contiguous(),
@@ -289,8 +290,8 @@ class S2M2(nn.Module):
         u = "upsample_mask_1x"
         wd = self._w(f"{u}.conv_disp.0.weight").flip(2, 3).permute(1, 2, 3, 0).reshape(16, 9)      # [co][tap]
         wr = self._w(f"{u}.conv_rgb.0.weight").flip(2, 3).permute(1, 2, 3, 0).reshape(16, 27)     # [co][tap*3+ci]
-        P["u1"] = {"wd": wd.float().contiguous(), "bd": f32c(f"{u}.conv_disp.0.bias"),
-                   "wr": wr.float().contiguous(), "br": f32c(f"{u}.conv_rgb.0.bias"),
+        P["u1"] = {"wd": hostc(wd), "bd": hostc(self._w(f"{u}.conv_disp.0.bias")),
+                   "wr": hostc(wr), "br": hostc(self._w(f"{u}.conv_rgb.0.bias")),
                    "ctx": self._convT2(f"{u}.conv_ctx"), "c0": self._conv(f"{u}.conv_concat.0", cin_to=64, cout_to=64),
                    "c2": self._convT1(f"{u}.conv_concat.2", cin_to=64, cout_to=16)}
         return P

@@ -332,8 +332,9 @@ def test_fused_stem_and_mask1x_inputs(ops, dtype):
     B, H, W = 2, 10, 14
     l = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
     r = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
-    w0, b0 = _rand((16, 3), torch.float32, g, 0.5), _rand((16,), torch.float32, g, 0.5)
-    w1, b1 = _rand((16, 16), torch.float32, g, 0.25), _rand((16,), torch.float32, g, 0.25)
+    cpu = lambda shape, sc: (torch.randn(shape, generator=g) * sc).contiguous()     # host tensors: kernel parameters
+    w0, b0 = cpu((16, 3), 0.5), cpu((16,), 0.5)
+    w1, b1 = cpu((16, 16), 0.25), cpu((16,), 0.25)
     a = torch.zeros((2 * B, H, W, 16), dtype=dtype, device=DEV)
     b = torch.zeros_like(a)
     cu.stem(l, r, w0, b0, w1, b1, a)
@@ -342,8 +343,8 @@ def test_fused_stem_and_mask1x_inputs(ops, dtype):
     _close(a, b, *tol, "stem")
     up = _rand((B, H, W, 4), torch.float32, g, 20.0)
     rgb = _rand((B, H, W, 3), dtype, g)
-    wd, bd = _rand((16, 9), torch.float32, g, 0.3), _rand((16,), torch.float32, g, 0.3)
-    wr, br = _rand((16, 27), torch.float32, g, 0.2), _rand((16,), torch.float32, g, 0.2)
+    wd, bd = cpu((16, 9), 0.3), cpu((16,), 0.3)
+    wr, br = cpu((16, 27), 0.2), cpu((16,), 0.2)
     oa = torch.zeros((B, H, W, 64), dtype=dtype, device=DEV)
     ob = torch.zeros_like(oa)
     cu.mask1x_inputs(up, rgb, wd, bd, wr, br, oa[..., 0:32])

@@ -123,11 +123,14 @@ class TorchOps:
         out.copy_(((x / 255.0 - 0.5) * 2).permute(0, 2, 3, 1).to(out.dtype))
 
     def stem(self, left, right, w0, b0, w1, b1, out):
+        dev = left.device
+        w0, b0, w1, b1 = (t.to(dev) for t in (w0, b0, w1, b1))       # weights arrive as host tensors
         x = ((torch.cat([left, right], 0) / 255.0 - 0.5) * 2)
         h = F.gelu(F.conv2d(x, w0[:, :, None, None], b0))
         out.copy_(F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1).to(out.dtype))
 
     def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
+        wd, bd, wr, br = (t.to(up.device) for t in (wd, bd, wr, br))
         d = up[..., 0:1].float().permute(0, 3, 1, 2)
         a = F.relu(F.conv2d(d, wd.reshape(16, 3, 3, 1).permute(0, 3, 1, 2), bd, padding=1))
         r = F.relu(F.conv2d(rgb.float().permute(0, 3, 1, 2), wr.reshape(16, 3, 3, 3).permute(0, 3, 1, 2), br, padding=1))
