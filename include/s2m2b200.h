@@ -143,9 +143,11 @@ int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const fl
  * logits (B,4h,4w,logits_ld >= 9) fp32, first 9 channels used -> up (B,4h,4w,4) fp32 (4th channel 0). */
 int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits,
                                int32_t logits_ld, int32_t B, int32_t h, int32_t w, float* up, void* stream);
-/* 9-tap softmax filter at full resolution (s2m2.py:116-133,190-193): out (3,B,1,H,W) planar fp32. */
+/* 9-tap softmax filter at full resolution (s2m2.py:116-133,190-193): out (3,B,1,H,W) planar fp32.
+ * upsample2 != 0 = the output_upsample=True branch (s2m2.py:123-127,194-195): out (3,B,1,2H,2W), logits bilinearly
+ * interpolated x2 before the softmax, neighbourhood nearest x2, disparity doubled. */
 int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
-                      void* stream);
+                      int32_t upsample2, void* stream);
 
 const char* s2m2b200_last_error(void);
 /* Version / capability string, e.g. "s2m2b200 0.1 sm_100a tcgen05". */

@@ -29,13 +29,15 @@ CASES = {
     "tiny_c32_b2_neg_96x64": (32, 1, 2, 96, 64, False, 2, 3, 4, 1.0),
     "tiny_c64_ntr2_64x128": (64, 2, 1, 64, 128, True, 1, 5, 6, 1.0),
     "s_c128_96x160": (128, 1, 1, 96, 160, True, 3, 0, 1, 1.0),
+    "tiny_c32_up2_64x96": (32, 1, 1, 64, 96, True, 2, 7, 8, 1.0, True),     # output_upsample=True (s2m2.py:123-127,194-195)
 }
 
 
 def run_case(name, cfg):
-    C, NTR, B, H, W, pos, it, wseed, iseed, gain = cfg
+    C, NTR, B, H, W, pos, it, wseed, iseed, gain = cfg[:10]
+    up2 = bool(cfg[10]) if len(cfg) > 10 else False
     sd = random_state_dict(C, NTR, wseed, gain)
-    m = S2M2(C, 1, NTR, pos, False, it).eval()
+    m = S2M2(C, 1, NTR, pos, up2, it).eval()
     m.load_state_dict(sd, strict=True)
     left, right = synthetic_pair(B, H, W, iseed)
     taps = {}
@@ -55,7 +57,7 @@ def run_case(name, cfg):
         d, o, c = m(left, right)
     out = {"disp": d.numpy(), "occ": o.numpy(), "conf": c.numpy(),
            "cfg": np.array([C, NTR, B, H, W, int(pos), it, wseed, iseed], dtype=np.int64),
-           "gain": np.array([gain], dtype=np.float64)}
+           "gain": np.array([gain], dtype=np.float64), "up2": np.array([int(up2)], dtype=np.int64)}
     keep = ("cnn_backbone#0.0", "feat_pyramid#0.0", "feat_pyramid#0.3", "transformer#0.0",
             "disp_init#0.0", "disp_init#0.1", "disp_init#0.2", "disp_init#0.3", "global_refiner#0.0",
             "ctx_feat#0.0", "upsample_mask_4x_refine#0.0")

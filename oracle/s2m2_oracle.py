@@ -400,9 +400,13 @@ def upsample4x(x: Tensor, logits: Tensor) -> Tensor:
     return (xu * logits.softmax(dim=1)).sum(1, keepdim=True)
 
 
-def filter1x(x: Tensor, logits: Tensor) -> Tensor:
-    """S2M2.upsample1x with output_upsample=False, s2m2.py:116-133."""
-    return (unfold3x3(x) * logits.softmax(dim=1)).sum(1, keepdim=True)
+def filter1x(x: Tensor, logits: Tensor, output_upsample: bool = False) -> Tensor:
+    """S2M2.upsample1x, s2m2.py:116-133.  output_upsample=True: neighbourhood nearest x2, logits bilinear x2 (s2m2.py:123-127)."""
+    xu = unfold3x3(x)
+    if output_upsample:
+        xu = F.interpolate(xu, scale_factor=2, mode="nearest")
+        logits = F.interpolate(logits, scale_factor=2, mode="bilinear", align_corners=False)
+    return (xu * logits.softmax(dim=1)).sum(1, keepdim=True)
 
 
 def upsample_mask_4x(sd: SD, p: str, hidden: Tensor, feat2x: Tensor) -> Tensor:
@@ -427,7 +431,7 @@ def upsample_mask_1x(sd: SD, p: str, disp: Tensor, rgb: Tensor, ctx: Tensor) -> 
 # --------------------------------------------------------------------------
 @torch.no_grad()
 def forward(sd: SD, img0: Tensor, img1: Tensor, num_transformer: int, use_positivity: bool = True,
-            refine_iter: int = 3, taps: Optional[dict] = None):
+            refine_iter: int = 3, taps: Optional[dict] = None, output_upsample: bool = False):
     """S2M2.forward, s2m2.py:136-197.  img0/img1: (B,3,H,W) fp32 in [0,255], H,W multiples of 32.
 
     Returns (disparity, occlusion, confidence), each (B,1,H,W) fp32.
@@ -473,4 +477,7 @@ def forward(sd: SD, img0: Tensor, img1: Tensor, num_transformer: int, use_positi
     disp_up, occ_up, conf_up = upsample4x(disp * 4, m4), upsample4x(occ, m4), upsample4x(conf, m4)
     _tap(taps, "up4x.disp", disp_up)
     m1 = upsample_mask_1x(sd, "upsample_mask_1x", disp_up, i0, f2_0)
-    return filter1x(disp_up, m1), filter1x(occ_up, m1), filter1x(conf_up, m1)
+    d = filter1x(disp_up, m1, output_upsample)
+    if output_upsample:
+        d = 2 * d                                                     # s2m2.py:194-195
+    return d, filter1x(occ_up, m1, output_upsample), filter1x(conf_up, m1, output_upsample)

@@ -36,20 +36,24 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 //     pesum[q, 16:32] = .5 * sum_yj  My[q, yj] * pe_y[yq - yj + h - 1],   My[q, yj] = sum_xj P[q, (yj, xj)]
 // only needs the two marginals of P: Mx accumulates in registers (a thread always owns the same key columns),
 // My is one row-sum per tile.  The (N, N, 32) tensor of utils.py:32-60 never exists.
-template <int D, int FA_BK, bool PE>
+// VS > 1 splits the value / output channels of a head over VS CTAs (each recomputes S = Q K^T): keeps the fp32 output
+// accumulator in registers for d = 384 (XL level 0).
+template <int D, int FA_BK, bool PE, int VS>
 __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   constexpr int LDS = D + 8;               // padded row (halves): conflict-free ldmatrix
   constexpr int KS = D / 16;               // k-steps of QK^T
   constexpr int NG = FA_BK / 8;            // 8-key groups per tile
-  constexpr int OG = D / 8;                // 8-channel groups of the output
+  constexpr int DV = D / VS;               // value / output channels handled by this CTA
+  constexpr int LDV = DV + 8;
+  constexpr int OG = DV / 8;               // 8-channel groups of the output
   extern __shared__ __align__(16) __half sm[];
   __half* Qs = sm;                         // [FA_BQ][LDS]
-  __half* KV = Qs + FA_BQ * LDS;           // 2 stages x { K [FA_BK][LDS], V [FA_BK][LDS] }  (cp.async double buffer)
-  constexpr int STAGE = 2 * FA_BK * LDS;   // halves per stage
+  __half* KV = Qs + FA_BQ * LDS;           // 2 stages x { K [FA_BK][LDS], V [FA_BK][LDV] }  (cp.async double buffer)
+  constexpr int STAGE = FA_BK * (LDS + LDV);   // halves per stage
   float* My_raw = (float*)(KV + 2 * STAGE);     // PE: [FA_BQ][pe_h] row sums at the running max of that time
   float* M_at = My_raw + FA_BQ * (PE ? p.pe_h : 0);   // PE: [FA_BQ][pe_h] that running max
   float* Mxs = M_at + FA_BQ * (PE ? p.pe_h : 0);      // PE: [FA_BQ][FA_BK] x-marginal (written at the end)
-  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, s = blockIdx.z;
+  const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y / VS, vs = blockIdx.y % VS, s = blockIdx.z;
   const int s_kv = (s + p.kv_shift) % p.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __half* base = (const __half*)p.qkv;
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   const float sl2 = p.scale * 1.4426950408889634f;       // softmax in base 2
   const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
   const uint32_t k_addr0 = (uint32_t)__cvta_generic_to_shared(KV + ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8);
-  const uint32_t v_addr0 = (uint32_t)__cvta_generic_to_shared(KV + FA_BK * LDS + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+  const uint32_t v_addr0 = (uint32_t)__cvta_generic_to_shared(KV + FA_BK * LDS + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDV + (lane >> 4) * 8);
   const uint32_t kv_base = (uint32_t)__cvta_generic_to_shared(KV);
 
   float mxr[PE ? NG : 1][4];               // PE: x-marginal of P for rows g, g+8 at key columns 8*ng + 2t, +1
@@ -85,9 +89,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
       const int r = e / CH, c = (e % CH) * 8;
       const bool ok = k0 + r < kend;
       const __half* src = base + ((long long)s_kv * p.N + (ok ? k0 + r : 0)) * p.qkv_ld + head * D + c;
-      const uint32_t dk = kv_base + (uint32_t)(st * STAGE + r * LDS + c) * 2;
-      cp_async16(dk, src + p.C, ok);
-      cp_async16(dk + FA_BK * LDS * 2, src + 2 * p.C, ok);
+      cp_async16(kv_base + (uint32_t)(st * STAGE + r * LDS + c) * 2, src + p.C, ok);
+      if (c < DV)   // this CTA's slice of the value channels
+        cp_async16(kv_base + (uint32_t)(st * STAGE + FA_BK * LDS + r * LDV + c) * 2, src + 2 * p.C + vs * DV, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
 #pragma unroll
       for (int og = 0; og < OG; og += 2) {
         uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(v_addr + (kk * 16 * LDS + og * 8) * 2, b0, b1, b2, b3);
+        ldsm_x4_t(v_addr + (kk * 16 * LDV + og * 8) * 2, b0, b1, b2, b3);
         mma16816(o[og], a0, a1, a2, a3, b0, b1);
         mma16816(o[og + 1], a0, a1, a2, a3, b2, b3);
       }
@@ -235,25 +239,25 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   __half* outp = (__half*)p.out;
 #pragma unroll
   for (int og = 0; og < OG; ++og) {
-    const int c = head * D + og * 8 + (lane & 3) * 2;
+    const int c = head * D + vs * DV + og * 8 + (lane & 3) * 2;
     if (r0 < p.N) *(__half2*)(outp + ((long long)s * p.N + r0) * p.out_ld + c) = __floats2half2_rn(o[og][0] * i0, o[og][1] * i0);
     if (r1 < p.N) *(__half2*)(outp + ((long long)s * p.N + r1) * p.out_ld + c) = __floats2half2_rn(o[og][2] * i1, o[og][3] * i1);
   }
 }
 
-template <int D, bool PE>
+template <int D, bool PE, int VS = 1>
 static int launch_fa(const AttnP& p, cudaStream_t s) {
   constexpr int FA_BK = (D > 128) ? 32 : 64;   // keeps two CTAs per SM at d = 256
-  const size_t smem = (size_t)(FA_BQ + 4 * FA_BK) * (D + 8) * sizeof(__half) +
+  const size_t smem = (size_t)((FA_BQ + 2 * FA_BK) * (D + 8) + 2 * FA_BK * (D / VS + 8)) * sizeof(__half) +
                       (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
   S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attention_mma_kernel<D, FA_BK, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(attention_mma_kernel<D, FA_BK, PE, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  dim3 grid(cdiv(p.N, FA_BQ), p.heads, p.S);
-  attention_mma_kernel<D, FA_BK, PE><<<grid, FA_THREADS, smem, s>>>(p);
+  dim3 grid(cdiv(p.N, FA_BQ), p.heads * VS, p.S);
+  attention_mma_kernel<D, FA_BK, PE, VS><<<grid, FA_THREADS, smem, s>>>(p);
   S2M2_LAUNCH_OK("attention_mma");
   return 0;
 }
@@ -266,7 +270,7 @@ int attention_mma_supported(const AttnP& p) {
   }
   if (p.qkv_ld % 8 || p.out_ld % 2 || !aligned(p.qkv, 16) || !aligned(p.out, 4)) return 0;
   switch (p.d) {
-    case 16: case 32: case 64: case 96: case 128: case 192: case 256: return 1;
+    case 16: case 32: case 64: case 96: case 128: case 192: case 256: case 384: return 1;
     default: return 0;
   }
 }
@@ -288,6 +292,7 @@ int attention_mma_launch(const AttnP& p, cudaStream_t s) {
     case 128: return launch_fa<128, false>(p, s);
     case 192: return launch_fa<192, false>(p, s);
     case 256: return launch_fa<256, false>(p, s);
+    case 384: return launch_fa<384, false, 2>(p, s);
   }
   set_error("attention_mma: unsupported head dim %d", p.d);
   return -1;

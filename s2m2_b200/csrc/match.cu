@@ -245,6 +245,48 @@ __global__ void filter1x_kernel(const float4* __restrict__ up, const float* __re
   }
 }
 
+// output_upsample=True branch (s2m2.py:123-127,194-195): the 3x3 neighbourhood is taken at (Y/2, X/2) (nearest x2), the
+// 9 logits are bilinearly interpolated x2 (align_corners=False) BEFORE the softmax, disparity is doubled.
+__global__ void filter2x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int lld, int B, int H, int W,
+                                float* __restrict__ out) {
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)B * H2 * W2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W2);
+    long long t = i / W2;
+    int Y = (int)(t % H2);
+    long long b = t / H2;
+    const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* l00 = logits + ((b * H + y0) * W + x0) * lld;
+    const float* l01 = logits + ((b * H + y0) * W + x1) * lld;
+    const float* l10 = logits + ((b * H + y1) * W + x0) * lld;
+    const float* l11 = logits + ((b * H + y1) * W + x1) * lld;
+    float lg[9], wt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) lg[k] = hy * (hx * l00[k] + lx * l01[k]) + ly * (hx * l10[k] + lx * l11[k]);
+    softmax9(lg, wt);
+    const int cy = Y >> 1, cx = X >> 1;
+    float d = 0.f, o = 0.f, c = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = min(max(cy + dy, 0), H - 1), xx = min(max(cx + dx, 0), W - 1);
+        float4 v = up[(b * H + yy) * W + xx];
+        float wk = wt[(dy + 1) * 3 + dx + 1];
+        d += v.x * wk;
+        o += v.y * wk;
+        c += v.z * wk;
+      }
+    out[i] = 2.f * d;
+    out[total + i] = o;
+    out[2 * total + i] = c;
+  }
+}
+
 }  // namespace s2m2
 
 using namespace s2m2;
@@ -279,8 +321,15 @@ int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float*
 }
 
 int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
-                      void* stream) {
+                      int32_t upsample2, void* stream) {
   S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "filter1x: up must be 16-byte aligned, logits_ld >= 9");
+  if (upsample2) {
+    long long n2 = 4LL * B * H * W;
+    long long g2 = (n2 + 255) / 256;
+    filter2x_kernel<<<(int)(g2 > 148 * 64 ? 148 * 64 : g2), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, logits_ld, B, H, W, out);
+    S2M2_LAUNCH_OK("filter2x");
+    return 0;
+  }
   long long n = (long long)B * H * W;
   long long g = (n + 255) / 256;
   filter1x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, logits_ld, B, H, W, out);

@@ -43,8 +43,6 @@ class S2M2(nn.Module):
         super().__init__()
         if dim_expansion != 1:
             raise ValueError("only dim_expansion=1 is supported (the reference's load_model always passes 1)")
-        if output_upsample:
-            raise NotImplementedError("output_upsample=True (s2m2.py:123-127) is a 'next' row, see DESIGN.md")
         if precision not in ("fp32", "fp16"):
             raise ValueError("precision must be 'fp32' or 'fp16'")
         self.feature_channels = feature_channels
@@ -574,6 +572,7 @@ class S2M2(nn.Module):
         ops.mask1x_inputs(up, img[:B], u1["wd"], u1["bd"], u1["wr"], u1["br"], m1in[..., 0:32])
         self._c(f2_0, u1["ctx"], out=m1in[..., 32:48])
         m1 = self._c(self._c(m1in, u1["c0"], ACT_RELU), u1["c2"], out_dtype=f32)
-        out = ops.empty((3, B, 1, H, W), f32, dev)
-        ops.filter1x(up, m1, out)
+        sc = 2 if self.output_upsample else 1                            # s2m2.py:123-127,194-195
+        out = ops.empty((3, B, 1, sc * H, sc * W), f32, dev)
+        ops.filter1x(up, m1, out, self.output_upsample)
         return out[0], out[1], out[2]

@@ -292,9 +292,10 @@ class CudaOps:
         self._chk(self.lib.s2m2b200_upsample4x_convex(p(disp), p(occ), p(conf), p(logits), logits.shape[3], B, h, w, p(up),
                                                       self._stream()), "upsample4x_convex")
 
-    def filter1x(self, up, logits, out):
+    def filter1x(self, up, logits, out, upsample2=False):
         B, H, W, _ = up.shape
         if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.shape[3] < 9:
             raise ValueError("filter1x: logits must be contiguous fp32 (B,H,W,>=9)")
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), logits.shape[3], B, H, W, p(out), self._stream()), "filter1x")
+        self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), logits.shape[3], B, H, W, p(out), int(upsample2), self._stream()),
+                  "filter1x")

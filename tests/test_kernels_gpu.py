@@ -140,6 +140,7 @@ ATTN_CASES = [
     (8, 160, 1, 128, True, None),       # S level 0
     (4, 80, 2, 64, False, None),        # S level 1
     (2, 384, 1, 64, False, None),       # longest row the whole-row kernel takes
+    (2, 100, 1, 384, True, None),       # XL level 0 head dim (value channels split over two CTAs)
 ]
 
 
@@ -323,6 +324,10 @@ def test_convex_upsampling(ops):
     cu.filter1x(ub, l1, oa)
     th.filter1x(ub, l1, ob)
     _close(oa, ob, 2e-6, 2e-5, "filter1x")
+    o2a, o2b = torch.zeros((3, B, 1, 8 * h, 8 * w), device=DEV), torch.zeros((3, B, 1, 8 * h, 8 * w), device=DEV)
+    cu.filter1x(ub, l1, o2a, True)
+    th.filter1x(ub, l1, o2b, True)
+    _close(o2a, o2b, 2e-6, 4e-5, "filter1x output_upsample")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])

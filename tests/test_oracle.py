@@ -34,6 +34,16 @@ def test_oracle_matches_reference_golden(name):
         assert (taps[f"refiner.{i}.occ"] - ref_occ * mask).abs().max() < 2e-5
 
 
+def test_oracle_output_upsample_branch_matches_reference_golden():
+    from conftest import GOLDEN_UP2
+    cfg, g = load_golden(GOLDEN_UP2)
+    sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    d, o, c = O.forward(sd, left, right, cfg["NTR"], cfg["pos"], cfg["it"], None, True)
+    assert d.shape == g["disp"].shape == (cfg["B"], 1, 2 * cfg["H"], 2 * cfg["W"])
+    assert (d - g["disp"]).abs().max() < 2e-4 and (o - g["occ"]).abs().max() < 2e-5 and (c - g["conf"]).abs().max() < 2e-5
+
+
 def test_argmax_is_bit_exact_on_golden():
     """prob_max_ind (submodules.py:226) recovered from the golden disparity: disp = x - corr, integer part."""
     cfg, g = load_golden("tiny_c32_64x96")

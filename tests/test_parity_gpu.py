@@ -210,6 +210,22 @@ def test_xl_2432x2048_config_runs_and_matches_oracle():
     assert err.mean().item() < 5e-3
 
 
+def test_output_upsample_branch_matches_reference_golden():
+    from conftest import GOLDEN_UP2
+    cfg, g = load_golden(GOLDEN_UP2)
+    sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    for prec, tol in (("fp32", 2e-4), ("fp16", 2e-2)):
+        m = S2M2(cfg["C"], 1, cfg["NTR"], use_positivity=cfg["pos"], refine_iter=cfg["it"], precision=prec, output_upsample=True).eval()
+        m.my_load_state_dict(sd)
+        m = m.to(DEV)
+        d, o, c = (t.cpu() for t in m(left.to(DEV), right.to(DEV)))
+        assert d.shape == g["disp"].shape
+        print(f"output_upsample {prec}: EPE {(d - g['disp']).abs().mean().item():.3e} max {(d - g['disp']).abs().max().item():.3e}")
+        assert (d - g["disp"]).abs().mean() < tol
+        assert (o - g["occ"]).abs().mean() < tol and (c - g["conf"]).abs().mean() < tol
+
+
 def test_batch_independence_and_determinism():
     """Pairs are independent units: a batch of two identical pairs gives two identical results,
     equal to the single-pair result, and repeated calls are bit-identical."""

@@ -15,7 +15,8 @@ from torch_ops import TorchOps
 
 def _build(cfg, precision="fp32"):
     sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
-    m = S2M2(cfg["C"], 1, cfg["NTR"], use_positivity=cfg["pos"], refine_iter=cfg["it"], precision=precision).eval()
+    m = S2M2(cfg["C"], 1, cfg["NTR"], use_positivity=cfg["pos"], refine_iter=cfg["it"], precision=precision,
+             output_upsample=cfg.get("up2", False)).eval()
     m.my_load_state_dict(sd)
     m.ops = TorchOps()
     return m, sd
@@ -46,6 +47,18 @@ def test_schedule_matches_golden(name):
     assert (d - g["disp"]).abs().mean() < 5e-5
     assert (o - g["occ"]).abs().max() < 1e-4
     assert (c - g["conf"]).abs().max() < 1e-4
+
+
+def test_schedule_output_upsample_branch_matches_golden():
+    """output_upsample=True (s2m2.py:123-127,194-195): (B,1,2H,2W) outputs, disparity doubled."""
+    from conftest import GOLDEN_UP2
+    cfg, g = load_golden(GOLDEN_UP2)
+    m, sd = _build(cfg)
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    d, o, c = m(left, right)
+    assert d.shape == (cfg["B"], 1, 2 * cfg["H"], 2 * cfg["W"])
+    assert (d - g["disp"]).abs().max() < 5e-3 and (d - g["disp"]).abs().mean() < 2e-4
+    assert (o - g["occ"]).abs().max() < 1e-4 and (c - g["conf"]).abs().max() < 1e-4
 
 
 def test_schedule_stage_taps_match_oracle():

@@ -234,7 +234,13 @@ class TorchOps:
             up[..., c] = (xu * wts).sum(1)
         up[..., 3] = 0
 
-    def filter1x(self, up, logits, out):
-        wts = logits[..., :9].float().permute(0, 3, 1, 2).softmax(dim=1)
+    def filter1x(self, up, logits, out, upsample2=False):
+        lg = logits[..., :9].float().permute(0, 3, 1, 2)
+        if upsample2:
+            lg = F.interpolate(lg, scale_factor=2, mode="bilinear", align_corners=False)
+        wts = lg.softmax(dim=1)
         for c in range(3):
-            out[c] = (self._unfold(up[..., c].unsqueeze(1)) * wts).sum(1, keepdim=True)
+            xu = self._unfold(up[..., c].unsqueeze(1))
+            if upsample2:
+                xu = F.interpolate(xu, scale_factor=2, mode="nearest")
+            out[c] = (xu * wts).sum(1, keepdim=True) * (2.0 if (upsample2 and c == 0) else 1.0)
