@@ -109,7 +109,8 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W,
                         const S2m2Tensor* out, void* stream);
 
-/* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images -> (2B,H,W,16)
+/* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images -> (2B,H,W,C>=16; channels
+ * beyond 16 are written as zeros so that the 5x5 stride-2 conv that follows can take 64-channel tcgen05 k-blocks)
  * (s2m2.py:86-87, submodules.py:70-72,89).  w0 (16,3), w1 (16,16), biases (16): fp32 HOST pointers (they become kernel parameters). */
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream);

@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   }
 }
 
-template <int D, bool PE, int VS = 1>
+template <int D, bool PE, int VS = 1, int BK_OVERRIDE = 0>
 static int launch_fa(const AttnP& p, cudaStream_t s) {
-  constexpr int FA_BK = (D > 128) ? 32 : 64;   // keeps two CTAs per SM at d = 256
+  constexpr int FA_BK = BK_OVERRIDE ? BK_OVERRIDE : ((D > 128) ? 32 : 64);   // 32 keeps two CTAs per SM at d = 256
   const size_t smem = (size_t)((FA_BQ + 2 * FA_BK) * (D + 8) + 2 * FA_BK * (D / VS + 8)) * sizeof(__half) +
                       (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
   S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
@@ -265,7 +265,7 @@ static int launch_fa(const AttnP& p, cudaStream_t s) {
 int attention_mma_supported(const AttnP& p) {
   if (!p.qh || !p.oh) return 0;
   if (p.pesum) {  // PE variant: fp16 pesum, image rows as key tiles, head dims used at 1/32 resolution
-    if (!p.ph_half || p.pe_w > 64 || p.pe_h * p.pe_w != p.N || p.pe_h > 128) return 0;
+    if (!p.ph_half || p.pe_w > 128 || p.pe_h * p.pe_w != p.N || p.pe_h > 128) return 0;
     if (!(p.d == 16 || p.d == 32 || p.d == 64 || p.d == 96)) return 0;
   }
   if (p.qkv_ld % 8 || p.out_ld % 2 || !aligned(p.qkv, 16) || !aligned(p.out, 4)) return 0;
@@ -276,6 +276,14 @@ int attention_mma_supported(const AttnP& p) {
 }
 
 int attention_mma_launch(const AttnP& p, cudaStream_t s) {
+  if (p.pesum && p.pe_w > 64) {   // wide token grids (XL@2432x2048: 76 columns): one image row = one 128-key tile
+    switch (p.d) {
+      case 16: return launch_fa<16, true, 1, 128>(p, s);
+      case 32: return launch_fa<32, true, 1, 128>(p, s);
+      case 64: return launch_fa<64, true, 1, 128>(p, s);
+      case 96: return launch_fa<96, true, 1, 128>(p, s);
+    }
+  }
   if (p.pesum) {
     switch (p.d) {
       case 16: return launch_fa<16, true>(p, s);

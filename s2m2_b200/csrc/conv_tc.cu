@@ -626,7 +626,10 @@ int conv_tc_supported(const S2m2Conv* a) {
   if (x.dtype != S2M2_F16 || a->w_dtype != S2M2_F16) return 0;
   if (a->batch > 1) return 0;
   if (a->stride == 2) {
-    if (a->KH != 3 || a->KW != 3 || a->pad_h != 1 || a->pad_w != 1 || x.H % 2 || x.W % 2 || x2.ptr || a->shuffle2x2) return 0;
+    // odd square kernels with 'same' padding (3x3 pad 1: conv2_down; 5x5 pad 2: conv1_down) via the four parity views
+    if (a->KH != a->KW || (a->KH != 3 && a->KH != 5) || a->pad_h != a->KH / 2 || a->pad_w != a->KW / 2 || x.H % 2 || x.W % 2 || x2.ptr ||
+        a->shuffle2x2)
+      return 0;
   } else if (a->stride != 1) {
     return 0;
   }

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ lef
     }
 #pragma unroll
     for (int k = 0; k < 16; k += 4) st4(o.p, i * o.ld + k, o.half, make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]));
+    for (int k = 16; k < o.C; k += 4) st4(o.p, i * o.ld + k, o.half, make_float4(0.f, 0.f, 0.f, 0.f));   // zero channel padding
   }
 }
 
@@ -485,7 +486,8 @@ int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_
 
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
-  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 16 && vec4_ok(*out), "stem: output must be (2B,H,W,16), 4-aligned");
+  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C >= 16 && vec4_ok(*out),
+             "stem: output must be (2B,H,W,>=16), 4-aligned (channels beyond 16 are zero-filled)");
   StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
   memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
   stem_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, hw, tv(*out));

@@ -244,7 +244,9 @@ class S2M2(nn.Module):
         hostc = lambda t: t.detach().float().cpu().contiguous()      # tiny weights that travel as kernel parameters
         P["bb"] = {"w0": hostc(self._w(f"{b}.conv0.0.weight").reshape(16, 3)), "b0": hostc(self._w(f"{b}.conv0.0.bias")),
                    "w1": hostc(self._w(f"{b}.conv0.2.weight").reshape(16, 16)), "b1": hostc(self._w(f"{b}.conv0.2.bias")),
-                   "d0": self._conv(f"{b}.conv1_down.0", stride=2), "d2": self._conv(f"{b}.conv1_down.2"),
+                   # fp16: the 16 stem channels are zero-padded to 64 so the 5x5 stride-2 conv runs on the tcgen05 kernel
+                   "d0": self._conv(f"{b}.conv1_down.0", stride=2, cin_to=64 if self.precision == "fp16" else None),
+                   "d2": self._conv(f"{b}.conv1_down.2"),
                    "gn_w": self._w(f"{b}.norm1.weight").float().contiguous(),
                    "gn_b": self._w(f"{b}.norm1.bias").float().contiguous(),
                    "c20": self._conv(f"{b}.conv2.0"), "c22": self._conv(f"{b}.conv2.2"),
@@ -460,7 +462,7 @@ class S2M2(nn.Module):
 
         # -- CNN backbone (submodules.py:88-93)
         bb = P["bb"]
-        x = ops.empty((2 * B, H, W, 16), adt, dev)
+        x = ops.empty((2 * B, H, W, bb["d0"].cin), adt, dev)
         ops.stem(img0.float().contiguous(), img1.float().contiguous(), bb["w0"], bb["b0"], bb["w1"], bb["b1"], x)
         x = self._c(self._c(x, bb["d0"], ACT_GELU), bb["d2"])
         x2 = self._new(x, C)

@@ -29,6 +29,7 @@ CASES = [
     (2, 32, 38, 512, 0, 512, 3, 3, ACT_NONE, False, False, False, 0),     # 1/32-res style 3x3, K=4608
     (2, 24, 36, 128, 0, 128, 3, 3, ACT_NONE, False, False, False, 0, 2),  # 3x3 stride 2 (conv2_down) via parity views
     (1, 64, 76, 256, 0, 256, 3, 3, ACT_GELU, False, False, False, 0, 2),  # 3x3 stride 2, N=256
+    (2, 48, 72, 64, 0, 64, 5, 5, ACT_GELU, False, False, False, 0, 2),    # 5x5 stride 2 (conv1_down.0 with padded channels)
 ]
 
 

@@ -130,6 +130,7 @@ ATTN_CASES = [
     (2, 5 * 9, 8, 32, False, (5, 9)),
     (2, 15 * 20, 8, 32, False, (15, 20)),       # S@640x480 pyramid PE block
     (2, 32 * 38, 8, 64, False, (32, 38)),       # L@1216x1024 pyramid PE block
+    (2, 20 * 76, 4, 96, False, (20, 76)),       # XL-style wide token grid (76 columns -> 128-key tiles)
     (2, 100, 8, 4, False, None),
     (3, 70, 1, 256, False, None),
     (2, 50, 2, 96, True, None),
@@ -340,7 +341,7 @@ def test_fused_stem_and_mask1x_inputs(ops, dtype):
     cpu = lambda shape, sc: (torch.randn(shape, generator=g) * sc).contiguous()     # host tensors: kernel parameters
     w0, b0 = cpu((16, 3), 0.5), cpu((16,), 0.5)
     w1, b1 = cpu((16, 16), 0.25), cpu((16,), 0.25)
-    a = torch.zeros((2 * B, H, W, 16), dtype=dtype, device=DEV)
+    a = torch.full((2 * B, H, W, 64), 5.0, dtype=dtype, device=DEV)       # channels 16..63 must come back as zeros
     b = torch.zeros_like(a)
     cu.stem(l, r, w0, b0, w1, b1, a)
     th.stem(l, r, w0, b0, w1, b1, b)

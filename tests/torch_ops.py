@@ -127,7 +127,8 @@ class TorchOps:
         w0, b0, w1, b1 = (t.to(dev) for t in (w0, b0, w1, b1))       # weights arrive as host tensors
         x = ((torch.cat([left, right], 0) / 255.0 - 0.5) * 2)
         h = F.gelu(F.conv2d(x, w0[:, :, None, None], b0))
-        out.copy_(F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1).to(out.dtype))
+        out.zero_()
+        out[..., :16] = F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1).to(out.dtype)
 
     def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
         wd, bd, wr, br = (t.to(up.device) for t in (wd, bd, wr, br))
