@@ -85,6 +85,12 @@ int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, 
 /* Scratch bytes the tcgen05 attention kernel needs for (S sequences, N tokens, heads, head dim d); 0 = not applicable. */
 int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, int32_t d, int32_t dtype);
 
+/* Fused pre-norm FFN (attentions.py:229-250): y = x + W2 . GELU(W0 . LayerNorm(x) + b0) + b2, one tcgen05 kernel that
+ * keeps LN(x) and the hidden activations in shared memory.  x, y: (.., C) fp16 views (y may alias x); w0, w2: (C, C)
+ * K-major fp16; b0, b2 fp32.  Returns 0 = launched, 1 = not applicable (caller runs layernorm + two conv2d), < 0 = error. */
+int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void* w0, const float* b0, const void* w2, const float* b2,
+                 int32_t w_dtype, void* stream);
+
 /* Relative-PE table of utils.py:32-60 for one axis of length n: HOST output (2n+1, 16) floats. */
 int s2m2b200_pe_table(int32_t n, float* host_out);
 

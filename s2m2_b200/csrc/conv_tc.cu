@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           uint4 a = make_uint4(0, 0, 0, 0), b = a;
           if (n < p.Cout) {
             const __half* rb = (const __half*)p.res + n + (odd ? 8 : 0);
-            if (ve) a = __ldg((const uint4*)(rb + row_e * p.res_ld));
-            if (vo) b = __ldg((const uint4*)(rb + row_o * p.res_ld));
+            if (ve) a = *(const uint4*)(rb + row_e * p.res_ld);   // plain loads: the output may alias the residual (z += f(z))
+            if (vo) b = *(const uint4*)(rb + row_o * p.res_ld);
           }
           // even lane holds (own.lo, partner.lo), odd lane holds (partner.hi, own.hi): swap the foreign halves
           const uint4 send = odd ? a : b;

@@ -329,6 +329,8 @@ class S2M2(nn.Module):
         return out
 
     def _ffn(self, z, p):
+        if self.ops.ffn(z, p["l0"], p["l2"]):        # fused tcgen05 kernel (fp16): LN, both GEMMs, GELU and the residual
+            return z
         h = self._c(self._ln(z), p["l0"], ACT_GELU)
         self._c(h, p["l2"], out=z, res=z)            # in place: z += ffn(LN(z))   (attentions.py:245-250)
         return z

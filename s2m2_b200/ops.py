@@ -52,7 +52,7 @@ def load_library():
 
 
 EXPORTS = [
-    "s2m2b200_conv2d", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
+    "s2m2b200_conv2d", "s2m2b200_ffn", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
@@ -87,6 +87,7 @@ class CudaOps:
         if conv_impl is None:
             conv_impl = int(os.environ.get("S2M2_CONV_IMPL", "0"))
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
+        self.ffn_fused = os.environ.get("S2M2_FFN_FUSED", "1") != "0"     # fused LN+FFN tcgen05 kernel
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
         self._pe = {}
         self._gn_work = {}
@@ -138,6 +139,18 @@ class CudaOps:
         a.batch, a.x_bs, a.w_bs, a.y_bs = batch, x_bs, w_bs, y_bs
         a.impl = self.conv_impl
         self._chk(self.lib.s2m2b200_conv2d(C.byref(a), self._stream()), f"conv2d[{cw.name}]")
+
+    def ffn(self, z, l0, l2):
+        """Fused LN -> Linear -> GELU -> Linear -> +z in place; False if the fused kernel does not take this shape/dtype."""
+        if not self.ffn_fused or l0.b is None or l2.b is None or l0.cin != l0.cout or l2.cin != l2.cout:
+            return False
+        zt = tview(z)
+        rc = self.lib.s2m2b200_ffn(C.byref(zt), C.byref(zt), C.c_void_p(l0.w.data_ptr()), C.c_void_p(l0.b.data_ptr()),
+                                   C.c_void_p(l2.w.data_ptr()), C.c_void_p(l2.b.data_ptr()), _DT[l0.w.dtype], self._stream())
+        if rc == 1:
+            return False
+        self._chk(rc, "ffn")
+        return True
 
     def row_corr(self, f, cv):
         """cv[b,y,i,j] = <f[b,y,i,:], f[B+b,y,j,:]>: one GEMM per scan-line (batched), fp32 (submodules.py:216-217)."""

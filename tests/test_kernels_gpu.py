@@ -356,3 +356,18 @@ def test_fused_stem_and_mask1x_inputs(ops, dtype):
     cu.mask1x_inputs(up, rgb, wd, bd, wr, br, oa[..., 0:32])
     th.mask1x_inputs(up, rgb, wd, bd, wr, br, ob[..., 0:32])
     _close(oa, ob, *((2e-5, 2e-4) if dtype == torch.float32 else (3e-3, 3e-2)), "mask1x_inputs")
+
+
+@pytest.mark.parametrize("C,M", [(256, 1000), (512, 300), (128, 2000), (384, 257), (192, 640), (256, 128 * 160)])
+def test_fused_ffn(ops, C, M):
+    """LN -> Linear -> GELU -> Linear -> +residual in one tcgen05 kernel vs the composite of torch ops (fp16 I/O)."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(C + M)
+    z = _rand((1, 1, M, C), torch.float16, g, 2.0) + 0.3
+    l0 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "l0")
+    l2 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "l2")
+    ref = th.ffn_reference(z, l0, l2)
+    za = z.clone()
+    assert cu.ffn(za, l0, l2), "fused FFN kernel refused a supported shape"
+    torch.cuda.synchronize()
+    _close(za, ref, 8e-3, 8e-3, f"fused ffn C={C} M={M}")

@@ -62,6 +62,16 @@ class TorchOps:
         assert out.shape == y.shape, (cw.name, out.shape, y.shape)
         out.copy_(y.to(out.dtype))
 
+    def ffn(self, z, l0, l2):
+        """The fused kernel's semantics (used by the GPU kernel test); returning False makes the schedule take the
+        LayerNorm + two conv2d route on CPU."""
+        return False
+
+    def ffn_reference(self, z, l0, l2):
+        zn = F.layer_norm(z.float(), (z.shape[3],)).to(z.dtype).float()
+        h = F.gelu(F.linear(zn, l0.w.float(), l0.b)).to(z.dtype).float()
+        return (F.linear(h, l2.w.float(), l2.b) + z.float()).to(z.dtype)
+
     def attention(self, qkv, o, S, N, heads, kv_shift, pe=None, pesum=None):
         C = o.shape[3]
         d = C // heads
