@@ -88,6 +88,7 @@ class CudaOps:
             conv_impl = int(os.environ.get("S2M2_CONV_IMPL", "0"))
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
         self.ffn_fused = os.environ.get("S2M2_FFN_FUSED", "1") != "0"     # fused LN+FFN tcgen05 kernel
+        self.ffn_min_tokens = int(os.environ.get("S2M2_FFN_MIN_TOKENS", "16384"))
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
         self._pe = {}
         self._gn_work = {}
@@ -143,6 +144,10 @@ class CudaOps:
     def ffn(self, z, l0, l2):
         """Fused LN -> Linear -> GELU -> Linear -> +z in place; False if the fused kernel does not take this shape/dtype."""
         if not self.ffn_fused or l0.b is None or l2.b is None or l0.cin != l0.cout or l2.cin != l2.cout:
+            return False
+        # the fused kernel runs one CTA per 128-token tile: below ~2 tiles per SM (1/16 and 1/32 resolution at L) the three
+        # separate launches, which also split the output channels over CTAs, are faster (measured, tools/bench_ffn.py)
+        if z.shape[0] * z.shape[1] * z.shape[2] < self.ffn_min_tokens:
             return False
         zt = tview(z)
         rc = self.lib.s2m2b200_ffn(C.byref(zt), C.byref(zt), C.c_void_p(l0.w.data_ptr()), C.c_void_p(l0.b.data_ptr()),

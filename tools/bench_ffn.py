@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Micro-benchmark: fused LN+FFN tcgen05 kernel vs LayerNorm + two conv2d launches, at the L@1216x1024 level shapes."""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from s2m2_b200.model import ACT_GELU, ACT_NONE, ConvW  # noqa: E402
+from s2m2_b200.ops import CudaOps  # noqa: E402
+
+SHAPES = [("level0 1/4", 155648, 256), ("level1 1/8", 38912, 256), ("level2 1/16", 9728, 512), ("level3 1/32", 2432, 512)]
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def main():
+    ops = CudaOps()
+    g = torch.Generator().manual_seed(0)
+    for name, M, C in SHAPES:
+        z = (torch.randn((1, 1, M, C), generator=g)).cuda().half()
+        mk = lambda: ConvW((torch.randn((C, C), generator=g) / math.sqrt(C)).cuda().half(), torch.randn((C,), generator=g).cuda(),
+                           1, 1, 1, 0, 0, C, C, False, "l")
+        l0, l2 = mk(), mk()
+        zn, h = torch.empty_like(z), torch.empty_like(z)
+
+        def unfused():
+            ops.layernorm(z, zn)
+            ops.conv2d(zn, l0, ACT_GELU, h)
+            ops.conv2d(h, l2, ACT_NONE, z, res=z)
+
+        t_f = timeit(lambda: ops.ffn(z, l0, l2))
+        t_u = timeit(unfused)
+        print(f"{name:14s} M={M:7d} C={C:4d}   fused {t_f:8.1f} us   LN+2 GEMMs {t_u:8.1f} us", flush=True)
+
+
+if __name__ == "__main__":
+    main()
