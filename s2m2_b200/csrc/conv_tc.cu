@@ -35,6 +35,7 @@ struct TcP {
   int KW, ph, pw, taps, stride;
   int cpb1, cpb2;        // 64-channel chunks per tap from x and x2
   int act, shuffle, Cr;
+  int tma_res;           // (with tma_store) the residual tile is TMA-loaded into the staging buffer instead of scattered global loads
   int tma_store;         // epilogue stages the tile in shared memory and writes it with cp.async.bulk.tensor (fp16, no scatter)
   int dbg;               // S2M2_TC_DBG experiments: 1 = no global stores, 2 = epilogue only drains (no math / stores)
 };
@@ -111,6 +112,7 @@ struct TcMaps {
   CUtensorMap act[4];
   CUtensorMap w;
   CUtensorMap out;   // v2 epilogue: box {BN/4 channels, 32 pixels of the tile} for the TMA store
+  CUtensorMap res;   // same box over the residual tensor
 };
 
 template <int BN, int STAGES>
@@ -316,8 +318,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   uint8_t* sB = smem + STAGES * A_BYTES;
   constexpr uint32_t STG_BYTES = 32 * (BN / TC2_EPI_GROUPS) * 2;          // per epilogue warp: 32 rows x CG fp16
   uint8_t* sStage = sB + STAGES * B_BYTES;                                  // 16 warps x STG_BYTES, 1024-aligned
-  uint64_t* bars = (uint64_t*)(sStage + 4 * TC2_EPI_GROUPS * 1024 * ((STG_BYTES + 1023) / 1024));  // full[S], empty[S], tfull[2], tempty[2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* bars = (uint64_t*)(sStage + 4 * TC2_EPI_GROUPS * 1024 * ((STG_BYTES + 1023) / 1024));  // full[S], empty[S], tfull[2], tempty[2], rbar[16]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4 + 4 * TC2_EPI_GROUPS);
+  const uint32_t rbar0 = smem_u32(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
@@ -335,6 +338,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4 * TC2_EPI_GROUPS);   // one arrive per epilogue warp
     }
+    for (int a = 0; a < 4 * TC2_EPI_GROUPS; ++a) mbar_init(rbar0 + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
     constexpr uint32_t SWZ_MASK = (CG * 2 >= 128) ? 7u : ((CG * 2 == 64) ? 3u : 1u);
     uint8_t* stg = sStage + (warp - 2) * STG_STRIDE;
     const uint32_t stg_u32 = smem_u32(stg);
-    uint32_t lt = 0;
+    uint32_t lt = 0, rt = 0;   // tiles processed, residual tiles loaded (phase of this warp's residual barrier)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       int n0, img, x0, y0;
       tile_coords(tile, n0, img, x0, y0);
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       constexpr int NCH = CG / 16;                       // 16-column chunks per warp
       uint4 rpre[NCH][2];
       const bool has_res = p.res != nullptr && !p.shuffle;
-      if (has_res && p.rh) {
+      if (has_res && p.rh && !p.tma_res) {
         // full-sector reads, same lane-pair trick as the stores: instruction 1 reads the even row of the pair (low half by
         // the even lane, high half by the odd lane), instruction 2 the odd row; one exchange puts the halves back in place.
         const bool odd = lane & 1;
@@ -471,12 +475,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         }
       }
       if (p.tma_store) {   // the previous tile's bulk store must have read the staging tile before it is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (p.tma_res && n0 + half * CG < p.Cout) {   // residual tile (same box as the store) -> staging buffer
+            const int r0 = q * 32;
+            int cx, cy;
+            if (p.flat) { cx = x0 + r0; cy = 0; }
+            else { cx = x0 + r0 % p.tw; cy = y0 + r0 / p.tw; }
+            mbar_expect_tx(rbar0 + 8 * (warp - 2), 32 * CG * 2);
+            tma_load_4d(&maps.res, stg_u32, rbar0 + 8 * (warp - 2), n0 + half * CG, cx, cy, img);
+          }
+        }
         __syncwarp();
       }
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (p.tma_res && n0 + half * CG < p.Cout) {
+        mbar_wait(rbar0 + 8 * (warp - 2), rt & 1);
+        ++rt;
+      }
       if (p.dbg & 2) valid = false;
       // neighbour-lane exchange for full-sector stores (see below): lane l pairs with lane l^1
       const bool pvalid = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
@@ -528,7 +546,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           off = pix * p.y_ld + co;
         } else {
           off = opix * p.y_ld + n;
-          if (has_res && valid) {
+          if (p.tma_res) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t lin = (uint32_t)lane * (CG * 2) + (uint32_t)(c * 2 + u) * 16;
+              const uint4 rv = *(const uint4*)(stg + (lin ^ (((lin >> 7) & SWZ_MASK) << 4)));
+              const __half2* hr = (const __half2*)&rv;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hr[i]);
+                v[8 * u + 2 * i] += f.x; v[8 * u + 2 * i + 1] += f.y;
+              }
+            }
+          } else if (has_res && valid) {
             if (p.rh) {
               const __half2* hr = (const __half2*)&rpre[c][0];
 #pragma unroll
@@ -712,7 +742,7 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
 template <int BN, int STAGES>
 static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles, cudaStream_t s) {
   constexpr size_t stg = 4 * TC2_EPI_GROUPS * 1024 * ((32 * (BN / TC2_EPI_GROUPS) * 2 + 1023) / 1024);
-  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + stg + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + stg + (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   static int sms = 0;
@@ -811,8 +841,20 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
       CUresult r = get_encode()(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+      p.tma_res = (p.res && res.dtype == S2M2_F16 && !getenv("S2M2_TC_NO_TMA_RES")) ? 1 : 0;
+      if (p.tma_res) {
+        cuuint64_t rstr[3];
+        if (p.flat) { rstr[0] = (cuuint64_t)res.ld * 2; rstr[1] = rstr[0] * dims[1]; rstr[2] = rstr[1]; }
+        else { rstr[0] = (cuuint64_t)res.ld * 2; rstr[1] = rstr[0] * y.W; rstr[2] = rstr[1] * y.H; }
+        CUresult r2 = get_encode()(&maps.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(res.ptr), dims, rstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        S2M2_CHECK(r2 == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(residual) failed: %d", (int)r2);
+      } else {
+        maps.res = maps.out;
+      }
     } else {
       maps.out = maps.w;
+      maps.res = maps.w;
     }
     if (BN == 256) return launch_tc2<256, 3>(maps, p, (int)mtiles, nt, s);
     if (BN == 128) return launch_tc2<128, 5>(maps, p, (int)mtiles, nt, s);
