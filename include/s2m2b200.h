@@ -91,6 +91,12 @@ int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, 
 int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void* w0, const float* b0, const void* w2, const float* b2,
                  int32_t w_dtype, void* stream);
 
+/* Fused pre-norm projection (attentions.py:119-130,150-161: q/k/v = Linear(LayerNorm(x))): y = W . LayerNorm(x) + b with the
+ * normalised tile kept in shared memory as the A operand for every output-channel tile.  x: (.., C) fp16, C in {128,192,256};
+ * y: (.., N) fp16, N % 64 == 0; w: (N, C) K-major fp16; bias fp32 or NULL.  Returns 0 = launched, 1 = not applicable (caller
+ * runs layernorm + conv2d), < 0 = error. */
+int s2m2b200_ln_linear(const S2m2Tensor* x, const S2m2Tensor* y, const void* w, const float* bias, int32_t w_dtype, void* stream);
+
 /* Relative-PE table of utils.py:32-60 for one axis of length n: HOST output (2n+1, 16) floats. */
 int s2m2b200_pe_table(int32_t n, float* host_out);
 

@@ -339,7 +339,9 @@ class S2M2(nn.Module):
         """LN -> fused QKV GEMM -> attention -> proj + residual (attentions.py:33-54,77-96,119-161)."""
         C = z.shape[3]
         heads = p["heads"]
-        qkv = self._c(self._ln(z), p["qkv"])
+        qkv = self._new(z, p["qkv"].cout)
+        if not self.ops.ln_linear(z, p["qkv"], qkv):   # fused tcgen05 kernel (fp16, >= 16384 tokens): LN(z) stays in smem
+            self._c(self._ln(z), p["qkv"], out=qkv)
         o = self._new(z, C)
         pesum = None
         if pe is not None and "pe_proj" in p:

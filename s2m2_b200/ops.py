@@ -52,7 +52,7 @@ def load_library():
 
 
 EXPORTS = [
-    "s2m2b200_conv2d", "s2m2b200_ffn", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
+    "s2m2b200_conv2d", "s2m2b200_ffn", "s2m2b200_ln_linear", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
@@ -89,6 +89,8 @@ class CudaOps:
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
         self.ffn_fused = os.environ.get("S2M2_FFN_FUSED", "1") != "0"     # fused LN+FFN tcgen05 kernel
         self.ffn_min_tokens = int(os.environ.get("S2M2_FFN_MIN_TOKENS", "16384"))
+        self.ln_linear_fused = os.environ.get("S2M2_LNL_FUSED", "1") != "0"  # fused LN + QKV projection tcgen05 kernel
+        self.ln_linear_min_tokens = int(os.environ.get("S2M2_LNL_MIN_TOKENS", "16384"))
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
         self._pe = {}
         self._gn_work = {}
@@ -155,6 +157,19 @@ class CudaOps:
         if rc == 1:
             return False
         self._chk(rc, "ffn")
+        return True
+
+    def ln_linear(self, z, lin, out):
+        """out = Linear(LayerNorm(z)) in one tcgen05 kernel (LN(z) never leaves shared memory); False if not applicable."""
+        if not self.ln_linear_fused or lin.kh != 1 or lin.kw != 1 or lin.shuffle:
+            return False
+        if z.shape[0] * z.shape[1] * z.shape[2] < self.ln_linear_min_tokens:
+            return False
+        rc = self.lib.s2m2b200_ln_linear(C.byref(tview(z)), C.byref(tview(out)), C.c_void_p(lin.w.data_ptr()),
+                                         C.c_void_p(lin.b.data_ptr() if lin.b is not None else None), _DT[lin.w.dtype], self._stream())
+        if rc == 1:
+            return False
+        self._chk(rc, "ln_linear")
         return True
 
     def row_corr(self, f, cv):

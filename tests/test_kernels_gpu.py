@@ -372,3 +372,22 @@ def test_fused_ffn(ops, C, M):
     assert cu.ffn(za, l0, l2), "fused FFN kernel refused a supported shape"
     torch.cuda.synchronize()
     _close(za, ref, 8e-3, 8e-3, f"fused ffn C={C} M={M}")
+
+
+@pytest.mark.parametrize("C,N,M,bias", [(256, 768, 1000, True), (128, 384, 2000, False), (192, 576, 640, True), (256, 768, 128 * 160, False),
+                                        (128, 64, 129, True), (256, 320, 4096, True)])
+def test_fused_ln_linear(ops, C, N, M, bias):
+    """LayerNorm -> Linear (the QKV projection) in one tcgen05 kernel vs torch (fp16 I/O, fp32 accumulate)."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(C + N + M)
+    z = _rand((1, 1, M, C), torch.float16, g, 2.0) + 0.3
+    lin = ConvW(_rand((N, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((N,), torch.float32, g, 0.3) if bias else None, 1, 1, 1, 0, 0, C, N,
+                False, "qkv")
+    ref = th.ln_linear_reference(z, lin)
+    big = torch.full((1, 1, M, N + 8), 7.0, dtype=torch.float16, device=DEV)     # strided view: ld = N + 8, guard columns
+    out = big[..., :N]
+    cu.ln_linear_min_tokens = 0
+    assert cu.ln_linear(z, lin, out), "fused LN+Linear kernel refused a supported shape"
+    torch.cuda.synchronize()
+    _close(out, ref, 6e-3, 6e-3, f"ln_linear C={C} N={N} M={M}")
+    assert bool((big[..., N:] == 7.0).all()), "ln_linear wrote outside its view"

@@ -67,6 +67,14 @@ class TorchOps:
         LayerNorm + two conv2d route on CPU."""
         return False
 
+    def ln_linear(self, z, lin, out):
+        """Returning False makes the schedule take the LayerNorm + conv2d route on CPU."""
+        return False
+
+    def ln_linear_reference(self, z, lin):
+        zn = F.layer_norm(z.float(), (z.shape[3],)).to(z.dtype).float()
+        return F.linear(zn, lin.w.float(), lin.b).to(z.dtype)
+
     def ffn_reference(self, z, l0, l2):
         zn = F.layer_norm(z.float(), (z.shape[3],)).to(z.dtype).float()
         h = F.gelu(F.linear(zn, l0.w.float(), l0.b)).to(z.dtype).float()

@@ -45,6 +45,18 @@ def main():
         t_f = timeit(lambda: ops.ffn(z, l0, l2))
         t_u = timeit(unfused)
         print(f"{name:14s} M={M:7d} C={C:4d}   fused {t_f:8.1f} us   LN+2 GEMMs {t_u:8.1f} us", flush=True)
+        if C <= 256:
+            qw = ConvW((torch.randn((3 * C, C), generator=g) / math.sqrt(C)).cuda().half(), None, 1, 1, 1, 0, 0, C, 3 * C, False, "qkv")
+            qkv = torch.empty((1, 1, M, 3 * C), dtype=torch.float16, device="cuda")
+            ops.ln_linear_min_tokens = 0
+
+            def unfused_q():
+                ops.layernorm(z, zn)
+                ops.conv2d(zn, qw, ACT_NONE, qkv)
+
+            t_f = timeit(lambda: ops.ln_linear(z, qw, qkv))
+            t_u = timeit(unfused_q)
+            print(f"{'':14s} LN+QKV  N={3 * C:4d}   fused {t_f:8.1f} us   LN+GEMM    {t_u:8.1f} us", flush=True)
 
 
 if __name__ == "__main__":
