@@ -3,12 +3,23 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace s2m2 {
 
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+
+bool pdl_enabled() {   // S2M2_PDL=1 turns programmatic dependent launch on.  Default off: inside the captured CUDA graph the
+  static int on = -1;  // kernel-to-kernel gaps are already hidden and the measured forward time did not improve (34.1 vs 34.3 ms).
+  if (on < 0) {
+    const char* e = getenv("S2M2_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -12,6 +12,7 @@ constexpr int AT_BQ = 32, AT_BK = 32, AT_THREADS = 256, AT_QPW = 4;  // 8 warps 
 
 template <int MAXI>  // MAXI = ceil(d / 32)
 __global__ void __launch_bounds__(AT_THREADS) attention_simt_kernel(AttnP p) {
+  pdl_sync();
   extern __shared__ __align__(16) float smem[];
   const int d = p.d, dp = d + 4;  // padded row (keeps 16 B alignment, conflict-free float4 rows)
   float* Qs = smem;               // [AT_BQ][dp]
@@ -170,7 +171,7 @@ static int launch_attn(const AttnP& p, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(cdiv(p.N, AT_BQ), p.heads, p.S);
-  attention_simt_kernel<MAXI><<<grid, AT_THREADS, smem, s>>>(p);
+  launch_k(attention_simt_kernel<MAXI>, grid, AT_THREADS, smem, s, p);
   S2M2_LAUNCH_OK("attention_simt");
   return 0;
 }

@@ -38,8 +38,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // My is one row-sum per tile.  The (N, N, 32) tensor of utils.py:32-60 never exists.
 // VS > 1 splits the value / output channels of a head over VS CTAs (each recomputes S = Q K^T): keeps the fp32 output
 // accumulator in registers for d = 384 (XL level 0).
+// K/V tiles are prefetched NST - 1 tiles ahead (cp.async ring): with ~2 CTAs per SM one tile of lookahead does not cover
+// the L2 round trip, two do (1/32-resolution 2-D attention: 44 -> see profiles).
+template <int D, int FA_BK, int VS>
+constexpr int fa_stages() { return ((64 + 3 * FA_BK) * (D + 8) + 3 * FA_BK * (D / VS + 8)) * 2 <= 120 * 1024 ? 3 : 2; }
+
 template <int D, int FA_BK, bool PE, int VS>
 __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
+  pdl_sync();
+  constexpr int NST = fa_stages<D, FA_BK, VS>();
   constexpr int LDS = D + 8;               // padded row (halves): conflict-free ldmatrix
   constexpr int KS = D / 16;               // k-steps of QK^T
   constexpr int NG = FA_BK / 8;            // 8-key groups per tile
@@ -48,9 +55,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
   constexpr int OG = DV / 8;               // 8-channel groups of the output
   extern __shared__ __align__(16) __half sm[];
   __half* Qs = sm;                         // [FA_BQ][LDS]
-  __half* KV = Qs + FA_BQ * LDS;           // 2 stages x { K [FA_BK][LDS], V [FA_BK][LDV] }  (cp.async double buffer)
+  __half* KV = Qs + FA_BQ * LDS;           // NST stages x { K [FA_BK][LDS], V [FA_BK][LDV] }  (cp.async ring)
   constexpr int STAGE = FA_BK * (LDS + LDV);   // halves per stage
-  float* My_raw = (float*)(KV + 2 * STAGE);     // PE: [FA_BQ][pe_h] row sums at the running max of that time
+  float* My_raw = (float*)(KV + NST * STAGE);     // PE: [FA_BQ][pe_h] row sums at the running max of that time
   float* M_at = My_raw + FA_BQ * (PE ? p.pe_h : 0);   // PE: [FA_BQ][pe_h] that running max
   float* Mxs = M_at + FA_BQ * (PE ? p.pe_h : 0);      // PE: [FA_BQ][FA_BK] x-marginal (written at the end)
   const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y / VS, vs = blockIdx.y % VS, s = blockIdx.z;
@@ -93,19 +100,22 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
       if (c < DV)   // this CTA's slice of the value channels
         cp_async16(kv_base + (uint32_t)(st * STAGE + FA_BK * LDS + r * LDV + c) * 2, src + 2 * p.C + vs * DV, ok);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // one commit group per tile slot, empty past the last tile, so that "all but the newest NST - 1 groups" is always tile i
   fetch(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if constexpr (NST == 3) {
+    if (kstep < p.N) fetch(kstep, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   for (int k0 = 0; k0 < p.N; k0 += kstep, ++tile_i) {
     const int kend = PE ? k0 + kstep : p.N;  // first key NOT in this tile
-    const int st = tile_i & 1;
-    if (k0 + kstep < p.N) {
-      fetch(k0 + kstep, st ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int st = tile_i % NST;
+    if (k0 + (NST - 1) * kstep < p.N) fetch(k0 + (NST - 1) * kstep, (tile_i + NST - 1) % NST);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if constexpr (NST == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
     const uint32_t k_addr = k_addr0 + st * STAGE * 2, v_addr = v_addr0 + st * STAGE * 2;
 
@@ -248,7 +258,9 @@ __global__ void __launch_bounds__(FA_THREADS) attention_mma_kernel(AttnP p) {
 template <int D, bool PE, int VS = 1, int BK_OVERRIDE = 0>
 static int launch_fa(const AttnP& p, cudaStream_t s) {
   constexpr int FA_BK = BK_OVERRIDE ? BK_OVERRIDE : ((D > 128) ? 32 : 64);   // 32 keeps two CTAs per SM at d = 256
-  const size_t smem = (size_t)((FA_BQ + 2 * FA_BK) * (D + 8) + 2 * FA_BK * (D / VS + 8)) * sizeof(__half) +
+  constexpr int NST = fa_stages<D, FA_BK, VS>();
+  static_assert(FA_BQ == 64, "fa_stages() assumes 64-query tiles");
+  const size_t smem = (size_t)((FA_BQ + NST * FA_BK) * (D + 8) + NST * FA_BK * (D / VS + 8)) * sizeof(__half) +
                       (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
   S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
   static bool attr = false;
@@ -257,7 +269,7 @@ static int launch_fa(const AttnP& p, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(cdiv(p.N, FA_BQ), p.heads * VS, p.S);
-  attention_mma_kernel<D, FA_BK, PE, VS><<<grid, FA_THREADS, smem, s>>>(p);
+  launch_k(attention_mma_kernel<D, FA_BK, PE, VS>, grid, FA_THREADS, smem, s, p);
   S2M2_LAUNCH_OK("attention_mma");
   return 0;
 }

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -320,7 +321,7 @@ static int launch_atc(const AtcMaps& maps, const AtcP& p, dim3 grid, size_t smem
     S2M2_CHECK(e == cudaSuccess, "attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr = true;
   }
-  attention_tc_kernel<D><<<grid, ATC_THREADS, smem, s>>>(maps, p);
+  launch_k(attention_tc_kernel<D>, grid, ATC_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("attention_tc");
   return 0;
 }

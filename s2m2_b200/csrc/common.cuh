@@ -31,6 +31,32 @@ extern long long g_launches;
     ++s2m2::g_launches;                                                             \
   } while (0)
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// With S2M2_PDL=1 every kernel is launched with the programmatic-stream-serialization attribute; each kernel runs
+// pdl_sync() before it touches global memory, so its CTAs may be scheduled (and run their shared-memory / TMEM / barrier
+// prologue) while the last wave of the previous kernel drains, then block until that kernel has completed and its writes
+// are visible.  Without the attribute (the default) both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError() in S2M2_LAUNCH_OK
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- dtype-agnostic element access ---------------------------------------------------------------

@@ -24,6 +24,7 @@ struct ConvP {
 
 template <int BM, int BN, int BK, int TM, int TN, bool VEC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) conv_simt_kernel(ConvP p) {
+  pdl_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int RM = TM / 4, RN = TN / 4;  // 4-wide register groups, spread over the tile to avoid bank conflicts
   constexpr int KV = BK / 4;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) conv_simt_kernel(Con
 // output channels from weights held in shared memory; 8-channel groups of one pixel are adjacent threads (coalesced).
 constexpr int SMALLK_MAX = 32;
 __global__ void __launch_bounds__(256) conv_smallk_kernel(ConvP p) {
+  pdl_sync();
   extern __shared__ float sw[];                  // [K][Cout] weights (transposed: lanes read consecutive channels) then [Cout] bias
   float* sb = sw + p.Cout * p.K;
   for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) {
@@ -300,8 +302,8 @@ template <int BM, int BN, int BK, int TM, int TN>
 static int launch_cfg(const ConvP& p, int batch, bool vec, cudaStream_t s) {
   dim3 grid(cdiv(p.M, BM), cdiv(p.Cout, BN), batch);
   dim3 block((BM / TM) * (BN / TN));
-  if (vec) conv_simt_kernel<BM, BN, BK, TM, TN, true><<<grid, block, 0, s>>>(p);
-  else conv_simt_kernel<BM, BN, BK, TM, TN, false><<<grid, block, 0, s>>>(p);
+  if (vec) launch_k(conv_simt_kernel<BM, BN, BK, TM, TN, true>, grid, block, 0, s, p);
+  else launch_k(conv_simt_kernel<BM, BN, BK, TM, TN, false>, grid, block, 0, s, p);
   S2M2_LAUNCH_OK("conv_simt");
   return 0;
 }
@@ -334,7 +336,7 @@ int conv_simt_launch(const S2m2Conv* a, cudaStream_t s) {
     long long g = (total + 255) / 256;
     if (g > 148LL * 32) g = 148LL * 32;
     const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout);
-    conv_smallk_kernel<<<(int)g, 256, smem, s>>>(p);
+    launch_k(conv_smallk_kernel, (int)g, 256, smem, s, p);
     S2M2_LAUNCH_OK("conv_smallk");
     return 0;
   }

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   // tile id -> coordinates (n-tile major: tile = nt * m_tiles + mt)
   auto tile_coords = [&](int tile, int& n0, int& img, int& x0, int& y0) {
@@ -734,7 +736,7 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(maps, p);
+  launch_k(conv_tc_kernel<BN, STAGES>, grid, TC_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("conv_tc");
   return 0;
 }
@@ -756,7 +758,7 @@ static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles
   }
   const long long tiles = (long long)m_tiles * n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  conv_tc_persistent_kernel<BN, STAGES><<<grid, TC2_THREADS, smem, s>>>(maps, p, m_tiles, n_tiles);
+  launch_k(conv_tc_persistent_kernel<BN, STAGES>, grid, TC2_THREADS, smem, s, maps, p, m_tiles, n_tiles);
   S2M2_LAUNCH_OK("conv_tc_persistent");
   return 0;
 }

@@ -25,6 +25,7 @@ static inline int grid_for(long long n, int block = 256) {
 // ------------------------------------------------------------------------------------------------
 template <int MAXI>
 __global__ void layernorm_kernel(TV x, TV y, const float* __restrict__ gamma, const float* __restrict__ beta, long long npix) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -65,6 +66,7 @@ __global__ void layernorm_kernel(TV x, TV y, const float* __restrict__ gamma, co
 // Deterministic (atomic-free) reduction: per-block partial sums in a fixed order, then a fixed-order final sum.
 // part: [N][nblk][groups][2] doubles, stats: [N][groups][2] doubles.
 __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, double* __restrict__ part) {
+  pdl_sync();
   extern __shared__ float sh[];  // [nw][C][2]
   const int n = blockIdx.y, C = x.C, cpg = C / groups;
   const int p0 = blockIdx.x * pix_per_block;
@@ -96,6 +98,7 @@ __global__ void gn_stats_kernel(TV x, int HW, int groups, int pix_per_block, dou
 // one warp per (n, g, k): lanes stride over the block partials, then a fixed shuffle tree -> deterministic
 // stats out: float2 (mean, rstd) per (n, g), computed once in double
 __global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int groups, int N, double cnt, float2* __restrict__ stats) {
+  pdl_sync();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // (n, g)
   if (i >= N * groups) return;
   const int g = i % groups, n = i / groups;
@@ -119,6 +122,7 @@ __global__ void gn_final_kernel(const double* __restrict__ part, int nblk, int g
 
 __global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const float2* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, long long total4) {
+  pdl_sync();
   const int C = x.C, C4 = C / 4, cpg = C / groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long pix = i / C4;
@@ -139,6 +143,7 @@ __global__ void gn_apply_kernel(TV x, TV y, int HW, int groups, const float2* __
 // resampling
 // ------------------------------------------------------------------------------------------------
 __global__ void avgpool2_kernel(TV x, TV y, int N, int H, int W, long long total4) {
+  pdl_sync();
   const int C4 = x.C / 4, Ho = H / 2, Wo = W / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long pix = i / C4;
@@ -158,6 +163,7 @@ __global__ void avgpool2_kernel(TV x, TV y, int N, int H, int W, long long total
 
 // bilinear x2, align_corners=False: src = (dst + .5)/2 - .5 clamped at 0 (torch semantics)
 __global__ void upsample2x_kernel(TV x, TV y, int N, int H, int W, long long total4) {
+  pdl_sync();
   const int C4 = x.C / 4, Ho = 2 * H, Wo = 2 * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long pix = i / C4;
@@ -189,6 +195,7 @@ enum { EW_COPY = 0, EW_UNARY = 1, EW_MUL = 2, EW_GRU = 3, EW_BLEND = 4 };
 
 template <int OP>
 __global__ void ew_kernel(TV a, TV b, TV c, TV d, TV o, int act, long long total4) {
+  pdl_sync();
   const int C4 = o.C / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     long long pix = i / C4;
@@ -220,6 +227,7 @@ __global__ void ew_kernel(TV a, TV b, TV c, TV d, TV o, int act, long long total
 }
 
 __global__ void preprocess_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W, TV o) {
+  pdl_sync();
   const long long HW = (long long)H * W, total = 2LL * B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long n = i / HW, hw = i - n * HW;
@@ -237,6 +245,7 @@ __global__ void preprocess_kernel(const float* __restrict__ left, const float* _
 struct StemW { float w0[48], b0[16], w1[256], b1[16]; };      // passed by value: constant bank, warp-uniform reads
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
                                                    const __grid_constant__ StemW wts, TV o) {
+  pdl_sync();
   const float* sw0 = wts.w0; const float* sb0 = wts.b0; const float* sw1 = wts.w1; const float* sb1 = wts.b1;
   const long long HW = (long long)H * W, total = 2LL * B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -270,6 +279,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ lef
 struct Mask1xW { float wd[144], wr[432], bd[16], br[16]; };
 __global__ void __launch_bounds__(256) mask1x_inputs_kernel(const float4* __restrict__ up, TV rgb, int B, int H, int W,
                                                             const __grid_constant__ Mask1xW wts, TV o) {
+  pdl_sync();
   const float* swd = wts.wd; const float* swr = wts.wr; const float* sbd = wts.bd; const float* sbr = wts.br;
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -315,6 +325,7 @@ __device__ __forceinline__ float logit_eps(float x, float eps) {
 }
 
 __global__ void gr_prep_kernel(const float* __restrict__ disp, const float* __restrict__ conf, long long n, TV o) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float c = conf[i], m = c > 0.2f ? 1.f : 0.f;
     st1(o.p, i * o.ld + 0, o.half, disp[i] / 100.f * m);
@@ -324,6 +335,7 @@ __global__ void gr_prep_kernel(const float* __restrict__ disp, const float* __re
 
 __global__ void gr_merge_kernel(float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ upd,
                                 long long upd_ld, long long n, int pos) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float m = conf[i] > 0.2f ? 1.f : 0.f;
     float d = m * disp[i] + (1.f - m) * upd[i * upd_ld];
@@ -333,6 +345,7 @@ __global__ void gr_merge_kernel(float* __restrict__ disp, const float* __restric
 
 __global__ void lr_prep_kernel(const float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ occ,
                                long long n, float4* __restrict__ small) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     small[i] = make_float4(disp[i] / 100.f, logit_eps(conf[i], 0.01f), logit_eps(occ[i], 0.01f), 0.f);
 }
@@ -340,6 +353,7 @@ __global__ void lr_prep_kernel(const float* __restrict__ disp, const float* __re
 __global__ void lr_update_kernel(float* __restrict__ disp, float* __restrict__ conf, float* __restrict__ occ,
                                  const float4* __restrict__ small, const float* __restrict__ upd, long long upd_ld,
                                  long long n, int w, int pos) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float4 s = small[i];
     const float* u = upd + i * upd_ld;   // [delta disp, delta conf logit, delta occ logit, ...]
@@ -369,10 +383,10 @@ int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* ga
   long long n = npix(*x);
   int block = 256, grid = grid_for(n * 32, block);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x->C <= 128) layernorm_kernel<4><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
-  else if (x->C <= 256) layernorm_kernel<8><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
-  else if (x->C <= 512) layernorm_kernel<16><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
-  else layernorm_kernel<32><<<grid, block, 0, s>>>(tv(*x), tv(*y), gamma, beta, n);
+  if (x->C <= 128) launch_k(layernorm_kernel<4>, grid, block, 0, s, tv(*x), tv(*y), gamma, beta, n);
+  else if (x->C <= 256) launch_k(layernorm_kernel<8>, grid, block, 0, s, tv(*x), tv(*y), gamma, beta, n);
+  else if (x->C <= 512) launch_k(layernorm_kernel<16>, grid, block, 0, s, tv(*x), tv(*y), gamma, beta, n);
+  else launch_k(layernorm_kernel<32>, grid, block, 0, s, tv(*x), tv(*y), gamma, beta, n);
   S2M2_LAUNCH_OK("layernorm");
   return 0;
 }
@@ -391,13 +405,13 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
   dim3 grid(nblk, x->N);
   const size_t smem = sizeof(float) * 2 * 8 * x->C;
   S2M2_CHECK(smem <= 48 * 1024, "groupnorm: C=%d too large", x->C);
-  gn_stats_kernel<<<grid, 256, smem, s>>>(tv(*x), HW, groups, ppb, part);
+  launch_k(gn_stats_kernel, grid, 256, smem, s, tv(*x), HW, groups, ppb, part);
   S2M2_LAUNCH_OK("gn_stats");
-  gn_final_kernel<<<cdiv((long long)x->N * groups * 32, 128), 128, 0, s>>>(part, nblk, groups, x->N, (double)HW * (x->C / groups),
+  launch_k(gn_final_kernel, cdiv((long long)x->N * groups * 32, 128), 128, 0, s, part, nblk, groups, x->N, (double)HW * (x->C / groups),
                                                                            (float2*)stats);
   S2M2_LAUNCH_OK("gn_final");
   long long total4 = npix(*x) * (x->C / 4);
-  gn_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tv(*x), tv(*y), HW, groups, (const float2*)stats, gamma, beta, total4);
+  launch_k(gn_apply_kernel, grid_for(total4), 256, 0, s, tv(*x), tv(*y), HW, groups, (const float2*)stats, gamma, beta, total4);
   S2M2_LAUNCH_OK("gn_apply");
   return 0;
 }
@@ -407,7 +421,7 @@ int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
              "avgpool2: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "avgpool2: needs C,ld multiples of 4 and aligned bases");
   long long total4 = npix(*y) * (y->C / 4);
-  avgpool2_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*y), x->N, x->H, x->W, total4);
+  launch_k(avgpool2_kernel, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*x), tv(*y), x->N, x->H, x->W, total4);
   S2M2_LAUNCH_OK("avgpool2");
   return 0;
 }
@@ -416,7 +430,7 @@ int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) 
   S2M2_CHECK(x->C == y->C && y->H == x->H * 2 && y->W == x->W * 2 && x->N == y->N, "upsample2x: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "upsample2x: needs C,ld multiples of 4 and aligned bases");
   long long total4 = npix(*y) * (y->C / 4);
-  upsample2x_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*y), x->N, x->H, x->W, total4);
+  launch_k(upsample2x_kernel, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*x), tv(*y), x->N, x->H, x->W, total4);
   S2M2_LAUNCH_OK("upsample2x");
   return 0;
 }
@@ -435,7 +449,7 @@ int s2m2b200_gate_blend(const S2m2Tensor* f, const S2m2Tensor* g, const S2m2Tens
   const S2m2Tensor* ins[4] = {f, g, z0, z1};
   if (int r = ew_check(out, ins, 4, "gate_blend")) return r;
   long long total4 = npix(*out) * (out->C / 4);
-  ew_kernel<EW_BLEND><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*f), tv(*g), tv(*z0), tv(*z1), tv(*out), 0, total4);
+  launch_k(ew_kernel<EW_BLEND>, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*f), tv(*g), tv(*z0), tv(*z1), tv(*out), 0, total4);
   S2M2_LAUNCH_OK("gate_blend");
   return 0;
 }
@@ -444,7 +458,7 @@ int s2m2b200_copy_channels(const S2m2Tensor* src, const S2m2Tensor* dst, void* s
   const S2m2Tensor* ins[1] = {src};
   if (int r = ew_check(dst, ins, 1, "copy_channels")) return r;
   long long total4 = npix(*dst) * (dst->C / 4);
-  ew_kernel<EW_COPY><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*src), tv(*src), tv(*src), tv(*src), tv(*dst), 0, total4);
+  launch_k(ew_kernel<EW_COPY>, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*src), tv(*src), tv(*src), tv(*src), tv(*dst), 0, total4);
   S2M2_LAUNCH_OK("copy_channels");
   return 0;
 }
@@ -453,7 +467,7 @@ int s2m2b200_unary(const S2m2Tensor* x, const S2m2Tensor* y, int32_t act, void* 
   const S2m2Tensor* ins[1] = {x};
   if (int r = ew_check(y, ins, 1, "unary")) return r;
   long long total4 = npix(*y) * (y->C / 4);
-  ew_kernel<EW_UNARY><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*x), tv(*x), tv(*x), tv(*x), tv(*y), act, total4);
+  launch_k(ew_kernel<EW_UNARY>, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*x), tv(*x), tv(*x), tv(*x), tv(*y), act, total4);
   S2M2_LAUNCH_OK("unary");
   return 0;
 }
@@ -462,7 +476,7 @@ int s2m2b200_mul(const S2m2Tensor* a, const S2m2Tensor* b, const S2m2Tensor* out
   const S2m2Tensor* ins[2] = {a, b};
   if (int r = ew_check(out, ins, 2, "mul")) return r;
   long long total4 = npix(*out) * (out->C / 4);
-  ew_kernel<EW_MUL><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*a), tv(*b), tv(*a), tv(*a), tv(*out), 0, total4);
+  launch_k(ew_kernel<EW_MUL>, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*a), tv(*b), tv(*a), tv(*a), tv(*out), 0, total4);
   S2M2_LAUNCH_OK("mul");
   return 0;
 }
@@ -471,7 +485,7 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
   const S2m2Tensor* ins[2] = {z, q};
   if (int r = ew_check(h, ins, 2, "gru_update")) return r;
   long long total4 = npix(*h) * (h->C / 4);
-  ew_kernel<EW_GRU><<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(tv(*z), tv(*q), tv(*z), tv(*z), tv(*h), 0, total4);
+  launch_k(ew_kernel<EW_GRU>, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*z), tv(*q), tv(*z), tv(*z), tv(*h), 0, total4);
   S2M2_LAUNCH_OK("gru_update");
   return 0;
 }
@@ -479,7 +493,7 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
                         void* stream) {
   S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 3, "preprocess: output must be (2B,H,W,3)");
-  preprocess_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, tv(*out));
+  launch_k(preprocess_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, tv(*out));
   S2M2_LAUNCH_OK("preprocess");
   return 0;
 }
@@ -490,7 +504,7 @@ int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, i
              "stem: output must be (2B,H,W,>=16), 4-aligned (channels beyond 16 are zero-filled)");
   StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
   memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
-  stem_kernel<<<grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(left, right, B, H, W, hw, tv(*out));
+  launch_k(stem_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, hw, tv(*out));
   S2M2_LAUNCH_OK("stem");
   return 0;
 }
@@ -501,7 +515,7 @@ int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* 
              "mask1x_inputs: rgb (B,H,W,3), out a 32-channel 4-aligned view, up 16-byte aligned");
   Mask1xW hw;   // wd/bd/wr/br are HOST pointers (2.4 KB of weights as a kernel parameter)
   memcpy(hw.wd, wd, sizeof(hw.wd)); memcpy(hw.bd, bd, sizeof(hw.bd)); memcpy(hw.wr, wr, sizeof(hw.wr)); memcpy(hw.br, br, sizeof(hw.br));
-  mask1x_inputs_kernel<<<grid_for(npix(*out)), 256, 0, (cudaStream_t)stream>>>((const float4*)up, tv(*rgb), rgb->N, rgb->H, rgb->W,
+  launch_k(mask1x_inputs_kernel, grid_for(npix(*out)), 256, 0, (cudaStream_t)stream, (const float4*)up, tv(*rgb), rgb->N, rgb->H, rgb->W,
                                                                                   hw, tv(*out));
   S2M2_LAUNCH_OK("mask1x_inputs");
   return 0;
@@ -509,7 +523,7 @@ int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* 
 
 int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n, const S2m2Tensor* out, void* stream) {
   S2M2_CHECK(out->C == 2 && npix(*out) == n, "global_refiner_prep: output must be a 2-channel view of npix pixels");
-  gr_prep_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, n, tv(*out));
+  launch_k(gr_prep_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, n, tv(*out));
   S2M2_LAUNCH_OK("global_refiner_prep");
   return 0;
 }
@@ -517,14 +531,14 @@ int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n
 int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t upd_ld, int64_t n, int32_t pos,
                                   void* stream) {
   S2M2_CHECK(upd_ld >= 1, "global_refiner_merge: bad upd_ld");
-  gr_merge_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, upd, upd_ld, n, pos);
+  launch_k(gr_merge_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, upd, upd_ld, n, pos);
   S2M2_LAUNCH_OK("global_refiner_merge");
   return 0;
 }
 
 int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const float* occ, int64_t n, float* small, void* stream) {
   S2M2_CHECK(aligned(small, 16), "local_refiner_prep: small must be 16-byte aligned");
-  lr_prep_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, n, (float4*)small);
+  launch_k(lr_prep_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, occ, n, (float4*)small);
   S2M2_LAUNCH_OK("local_refiner_prep");
   return 0;
 }
@@ -533,7 +547,7 @@ int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const fl
                                   int32_t B, int32_t h, int32_t w, int32_t pos, void* stream) {
   long long n = (long long)B * h * w;
   S2M2_CHECK(upd_ld >= 3, "local_refiner_update: upd needs >= 3 channels");
-  lr_update_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(disp, conf, occ, (const float4*)small, upd, upd_ld, n, w, pos);
+  launch_k(lr_update_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, occ, (const float4*)small, upd, upd_ld, n, w, pos);
   S2M2_LAUNCH_OK("local_refiner_update");
   return 0;
 }

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_tc_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -312,7 +313,7 @@ static int launch_ffn(const FfnMaps& maps, const FfnP& p, cudaStream_t s) {
     attr = true;
   }
   const int tiles = (p.M + 127) / 128;
-  ffn_tc_kernel<C><<<tiles < sms ? tiles : sms, FFN_THREADS, smem, s>>>(maps, p);
+  launch_k(ffn_tc_kernel<C>, tiles < sms ? tiles : sms, FFN_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("ffn_tc");
   return 0;
 }

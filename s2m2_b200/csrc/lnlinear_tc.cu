@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(LNL_THREADS, 1) lnlinear_tc_kernel(const __gri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -244,7 +245,7 @@ static int launch_lnl(const LnlMaps& maps, const LnlP& p, cudaStream_t s) {
     attr = true;
   }
   const int tiles = (p.M + 127) / 128;
-  lnlinear_tc_kernel<C><<<tiles < sms ? tiles : sms, LNL_THREADS, smem, s>>>(maps, p);
+  launch_k(lnlinear_tc_kernel<C>, tiles < sms ? tiles : sms, LNL_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("lnlinear_tc");
   return 0;
 }

@@ -23,6 +23,7 @@ __device__ __forceinline__ float sk_a(const float* __restrict__ row_i, int i, in
 __global__ void __launch_bounds__(SK_THREADS) sinkhorn_kernel(const float* __restrict__ cv, int w, int pos, int iters,
                                                                float* __restrict__ disp, float* __restrict__ conf,
                                                                float* __restrict__ occ, int* __restrict__ amax) {
+  pdl_sync();
   extern __shared__ float sh[];
   const int W1 = w + 1;
   float* u = sh;                 // [W1]
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 __global__ void cv_lookup_kernel(const float* __restrict__ cv, const float* __restrict__ disp, long long npix, int w,
                                  float* __restrict__ out) {
+  pdl_sync();
   const long long total = npix * 18;
   const int w2 = w / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +193,7 @@ __device__ __forceinline__ void softmax9(const float* __restrict__ l, float* wt)
 
 __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* __restrict__ occ, const float* __restrict__ conf,
                                   const float* __restrict__ logits, int lld, int B, int h, int w, float4* __restrict__ up) {
+  pdl_sync();
   const int H = 4 * h, W = 4 * w;
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -219,6 +222,7 @@ __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* _
 
 __global__ void filter1x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int lld, int B, int H, int W,
                                 float* __restrict__ out) {
+  pdl_sync();
   const long long total = (long long)B * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int X = (int)(i % W);
@@ -249,6 +253,7 @@ __global__ void filter1x_kernel(const float4* __restrict__ up, const float* __re
 // 9 logits are bilinearly interpolated x2 (align_corners=False) BEFORE the softmax, disparity is doubled.
 __global__ void filter2x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int lld, int B, int H, int W,
                                 float* __restrict__ out) {
+  pdl_sync();
   const int H2 = 2 * H, W2 = 2 * W;
   const long long total = (long long)B * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -297,7 +302,7 @@ int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t 
                                  int32_t* amax, int32_t use_positivity, int32_t iters, void* stream) {
   S2M2_CHECK(w >= 8 && w <= 8192 && iters >= 1, "sinkhorn: bad w=%d / iters=%d", w, iters);
   size_t smem = sizeof(float) * (2 * (w + 1) + 2 * SK_WARPS * 32);
-  sinkhorn_kernel<<<B * h, SK_THREADS, smem, (cudaStream_t)stream>>>(cv, w, use_positivity, iters, disp, conf, occ, amax);
+  launch_k(sinkhorn_kernel, B * h, SK_THREADS, smem, (cudaStream_t)stream, cv, w, use_positivity, iters, disp, conf, occ, amax);
   S2M2_LAUNCH_OK("sinkhorn_softargmax");
   return 0;
 }
@@ -305,7 +310,7 @@ int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t 
 int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h, int32_t w, float* out, void* stream) {
   long long n = (long long)B * h * w;
   long long g = (n * 18 + 255) / 256;
-  cv_lookup_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(cv, disp, n, w, out);
+  launch_k(cv_lookup_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, cv, disp, n, w, out);
   S2M2_LAUNCH_OK("cv_lookup");
   return 0;
 }
@@ -315,7 +320,7 @@ int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float*
   S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "upsample4x_convex: up must be 16-byte aligned, logits_ld >= 9");
   long long n = 16LL * B * h * w;
   long long g = (n + 255) / 256;
-  upsample4x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>(disp, occ, conf, logits, logits_ld, B, h, w, (float4*)up);
+  launch_k(upsample4x_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, disp, occ, conf, logits, logits_ld, B, h, w, (float4*)up);
   S2M2_LAUNCH_OK("upsample4x_convex");
   return 0;
 }
@@ -326,13 +331,13 @@ int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, i
   if (upsample2) {
     long long n2 = 4LL * B * H * W;
     long long g2 = (n2 + 255) / 256;
-    filter2x_kernel<<<(int)(g2 > 148 * 64 ? 148 * 64 : g2), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, logits_ld, B, H, W, out);
+    launch_k(filter2x_kernel, (int)(g2 > 148 * 64 ? 148 * 64 : g2), 256, 0, (cudaStream_t)stream, (const float4*)up, logits, logits_ld, B, H, W, out);
     S2M2_LAUNCH_OK("filter2x");
     return 0;
   }
   long long n = (long long)B * H * W;
   long long g = (n + 255) / 256;
-  filter1x_kernel<<<(int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream>>>((const float4*)up, logits, logits_ld, B, H, W, out);
+  launch_k(filter1x_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, (const float4*)up, logits, logits_ld, B, H, W, out);
   S2M2_LAUNCH_OK("filter1x");
   return 0;
 }
