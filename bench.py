@@ -6,7 +6,9 @@
   python bench.py --impl reference ...     (the reference algorithm's CPU path = the oracle port, host cores)
 
 A "step" is one forward over `batch` synthetic stereo pairs per GPU (random-init weights of the named
-architecture, synthetic images — there is no network for checkpoints/datasets).
+architecture, synthetic images — there is no network for checkpoints/datasets).  Default batch = 8 pairs per GPU
+(BASELINE config 5: batch 64 sharded over 8 GPUs, weak scaling keeps 8 per GPU at every N); the single-pair latency
+(config 3, the protocol of the reference's README FPS table) is reported beside it as `single_pair`.
   value      pairs/s with the inputs already resident in HBM (CUDA-graph replay of the whole forward),
              CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
   e2e        the same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of both
@@ -157,7 +159,8 @@ def main():
     ap.add_argument("--model", default="L", choices=["S", "M", "L", "XL"])
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=1216)
-    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=8,
+                    help="stereo pairs per GPU per step (default 8 = BASELINE config 5's share: batch 64 over 8 GPUs)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -272,6 +275,36 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
 
+        # ---- single-pair latency (BASELINE config 3, the protocol behind the reference's README FPS): batch 1, rank 0
+        single = None
+        if rank == 0 and B != 1:
+            l1, r1 = left[:1].clone(), right[:1].clone()
+            for _ in range(2):
+                model(l1, r1)
+            g1 = None
+            if not args.no_graph:
+                s1 = torch.cuda.Stream()
+                s1.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s1):
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1, stream=s1):
+                        model(l1, r1)
+                torch.cuda.current_stream().wait_stream(s1)
+            one = (lambda: g1.replay()) if g1 is not None else (lambda: model(l1, r1))
+            for _ in range(3):
+                one()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n1 = max(args.steps, 5)
+            torch.cuda.synchronize()
+            a0.record()
+            for _ in range(n1):
+                one()
+            a1.record()
+            torch.cuda.synchronize()
+            ms1 = a0.elapsed_time(a1) / n1
+            single = {"batch": 1, "ms_per_pair": ms1, "pairs_per_s": 1e3 / ms1, "steps": n1}
+            del g1
+
         # ---- roofline of the dominant kernel (implicit-GEMM conv), heaviest shape timed alone (rank 0)
         roof = None
         if rank == 0:
@@ -323,6 +356,8 @@ def main():
                     "d2h_bytes_per_step": 3 * B * H * W * 4},
             "gpu_launches": launches_per_fwd * args.steps, "launches_per_forward": launches_per_fwd,
             "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof}
+    if single:
+        line["single_pair"] = single
     if tf:
         ach = value / world * tf
         line["roofline_forward"] = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",

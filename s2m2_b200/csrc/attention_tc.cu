@@ -38,7 +38,7 @@ struct AtcMaps {
 };
 
 template <int D>
-constexpr int atc_stages() { return D >= 256 ? 2 : 4; }
+constexpr int atc_stages() { return D >= 256 ? 2 : 8; }   // ring slots of 64 keys x D channels; as many bytes in flight as fit
 
 __device__ __forceinline__ float ex2_approx(float x) {   // x <= 0 here: no range fix-up needed, denormal results flush to 0
   float y;
@@ -47,7 +47,7 @@ __device__ __forceinline__ float ex2_approx(float x) {   // x <= 0 here: no rang
 }
 
 static size_t atc_smem_bytes(int D, int NKB) {
-  const int NST = D >= 256 ? 2 : 4;
+  const int NST = D >= 256 ? 2 : 8;
   return (size_t)128 * D * 2 + (size_t)NKB * 16384 + (size_t)NST * 64 * D * 2 + (6 + 2 * NST) * 8 + 16 + 2 * ATC_SPLIT * 128 * 4 + 1024;
 }
 

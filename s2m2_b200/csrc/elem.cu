@@ -188,6 +188,138 @@ __global__ void upsample2x_kernel(TV x, TV y, int N, int H, int W, long long tot
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fp16 fast paths of the resampling / GroupNorm kernels: 8 channels (16 B) per thread, the channel slot is fixed per thread
+// (blockDim = C/8 x pixels-per-block), rows are dealt to blocks — no integer division in the pixel loop, full-sector accesses.
+// Same arithmetic as the generic kernels above.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __half2* h = (const __half2*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __half2* h = (__half2*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+__global__ void upsample2x_h8_kernel(const __half* __restrict__ x, long long xld, __half* __restrict__ y, long long yld, int N, int H, int W,
+                                     int C8, int PPB) {
+  pdl_sync();
+  const int c8 = threadIdx.x % C8, p0 = threadIdx.x / C8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0, hy = 1.f - ly;
+    const __half* r0 = x + ((long long)n * H + y0) * W * xld + c8 * 8;
+    const __half* r1 = x + ((long long)n * H + y1) * W * xld + c8 * 8;
+    __half* out = y + (long long)row * Wo * yld + c8 * 8;
+    for (int ox = p0; ox < Wo; ox += PPB) {
+      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, W - 1);
+      const float lx = sx - x0, hx = 1.f - lx;
+      float a[8], b[8], d[8], e[8], o[8];
+      unpack8(*(const uint4*)(r0 + x0 * xld), a); unpack8(*(const uint4*)(r0 + x1 * xld), b);
+      unpack8(*(const uint4*)(r1 + x0 * xld), d); unpack8(*(const uint4*)(r1 + x1 * xld), e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * d[k] + lx * e[k]);
+      *(uint4*)(out + ox * yld) = pack8(o);
+    }
+  }
+}
+
+__global__ void avgpool2_h8_kernel(const __half* __restrict__ x, long long xld, __half* __restrict__ y, long long yld, int N, int H, int W,
+                                   int C8, int PPB) {
+  pdl_sync();
+  const int c8 = threadIdx.x % C8, p0 = threadIdx.x / C8;
+  const int Ho = H / 2, Wo = W / 2;
+  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    const __half* r0 = x + ((long long)n * H + 2 * oy) * W * xld + c8 * 8;
+    const __half* r1 = r0 + (long long)W * xld;
+    __half* out = y + (long long)row * Wo * yld + c8 * 8;
+    for (int ox = p0; ox < Wo; ox += PPB) {
+      float a[8], b[8], d[8], e[8], o[8];
+      unpack8(*(const uint4*)(r0 + (2 * ox) * xld), a); unpack8(*(const uint4*)(r0 + (2 * ox + 1) * xld), b);
+      unpack8(*(const uint4*)(r1 + (2 * ox) * xld), d); unpack8(*(const uint4*)(r1 + (2 * ox + 1) * xld), e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (a[k] + b[k] + d[k] + e[k]) * 0.25f;
+      *(uint4*)(out + ox * yld) = pack8(o);
+    }
+  }
+}
+
+// GroupNorm statistics, fp16: block = (C/8) x PPB threads over a contiguous range of pixels of image blockIdx.y; partial sums per
+// block in a fixed order (deterministic), same `part` layout as gn_stats_kernel.
+__global__ void gn_stats_h8_kernel(const __half* __restrict__ x, long long xld, int HW, int C8, int PPB, int groups, int pix_per_block,
+                                   double* __restrict__ part) {
+  pdl_sync();
+  extern __shared__ float sh[];  // [PPB][C][2]
+  const int n = blockIdx.y, C = C8 * 8, cpg = C / groups;
+  const int c8 = threadIdx.x % C8, p0 = threadIdx.x / C8;
+  const int b0 = blockIdx.x * pix_per_block, b1 = min(b0 + pix_per_block, HW);
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+  const __half* base = x + (long long)n * HW * xld + c8 * 8;
+  for (int pp = b0 + p0; pp < b1; pp += PPB) {
+    float v[8];
+    unpack8(*(const uint4*)(base + pp * xld), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sh[(p0 * C + c8 * 8 + k) * 2 + 0] = s[k];
+    sh[(p0 * C + c8 * 8 + k) * 2 + 1] = q[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * groups) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    double acc = 0.0;
+    for (int w = 0; w < PPB; ++w)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += (double)sh[(w * C + c) * 2 + k];
+    part[(((long long)n * gridDim.x + blockIdx.x) * groups + g) * 2 + k] = acc;
+  }
+}
+
+__global__ void gn_apply_h8_kernel(const __half* __restrict__ x, long long xld, __half* __restrict__ y, long long yld, int HW, int C8, int PPB,
+                                   int groups, const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta) {
+  pdl_sync();
+  const int n = blockIdx.y, C = C8 * 8, cpg = C / groups;
+  const int c8 = threadIdx.x % C8, p0 = threadIdx.x / C8;
+  float mean[8], sc[8], sf[8];   // same operation order as the generic kernel: (v - mean) * rstd * gamma + beta
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c8 * 8 + k;
+    const float2 mr = __ldg(stats + (long long)n * groups + c / cpg);
+    mean[k] = mr.x; sc[k] = mr.y; sf[k] = beta[c];
+  }
+  float gm[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gm[k] = gamma[c8 * 8 + k];
+  const __half* xb = x + (long long)n * HW * xld + c8 * 8;
+  __half* yb = y + (long long)n * HW * yld + c8 * 8;
+  for (int pp = blockIdx.x * PPB + p0; pp < HW; pp += gridDim.x * PPB) {
+    float v[8];
+    unpack8(*(const uint4*)(xb + pp * xld), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean[k]) * sc[k] * gm[k] + sf[k];
+    *(uint4*)(yb + pp * yld) = pack8(v);
+  }
+}
+
+static inline bool h8_ok(const S2m2Tensor& t) {
+  return t.dtype == S2M2_F16 && t.C % 8 == 0 && t.C <= 2048 && t.ld % 8 == 0 && aligned(t.ptr, 16);
+}
+
 // ------------------------------------------------------------------------------------------------
 // element-wise (vector of 4 channels per thread)
 // ------------------------------------------------------------------------------------------------
@@ -244,7 +376,7 @@ __global__ void preprocess_kernel(const float* __restrict__ left, const float* _
 // stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16)   (s2m2.py:86-87, submodules.py:70-72)
 struct StemW { float w0[48], b0[16], w1[256], b1[16]; };      // passed by value: constant bank, warp-uniform reads
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
-                                                   const __grid_constant__ StemW wts, TV o) {
+                                                   const __grid_constant__ StemW wts, TV o, int s2d) {
   pdl_sync();
   const float* sw0 = wts.w0; const float* sb0 = wts.b0; const float* sw1 = wts.w1; const float* sb1 = wts.b1;
   const long long HW = (long long)H * W, total = 2LL * B * HW;
@@ -267,6 +399,14 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ lef
 #pragma unroll
       for (int j = 0; j < 16; ++j) t = fmaf(sw1[k * 16 + j], hdn[j], t);
       out[k] = t;
+    }
+    if (s2d) {   // space-to-depth: out[n, y/2, x/2, ((y&1)*2 + (x&1))*16 + k]  (fp16, 32 contiguous bytes per pixel)
+      const int yy = (int)(hw / W), xx = (int)(hw - (long long)yy * W);
+      const long long q = (n * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1);
+      __half* dst = (__half*)o.p + q * o.ld + ((yy & 1) * 2 + (xx & 1)) * 16;
+      *(uint4*)dst = pack8(out);
+      *(uint4*)(dst + 8) = pack8(out + 8);
+      continue;
     }
 #pragma unroll
     for (int k = 0; k < 16; k += 4) st4(o.p, i * o.ld + k, o.half, make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]));
@@ -403,13 +543,23 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
   double* stats = work;
   double* part = work + 2LL * x->N * groups;
   dim3 grid(nblk, x->N);
-  const size_t smem = sizeof(float) * 2 * 8 * x->C;
+  const bool h8 = h8_ok(*x) && h8_ok(*y) && x->C <= 512;
+  const int C8 = x->C / 8, PPB = h8 ? 256 / C8 : 8;
+  const size_t smem = sizeof(float) * 2 * PPB * x->C;
   S2M2_CHECK(smem <= 48 * 1024, "groupnorm: C=%d too large", x->C);
-  launch_k(gn_stats_kernel, grid, 256, smem, s, tv(*x), HW, groups, ppb, part);
+  if (h8) launch_k(gn_stats_h8_kernel, grid, C8 * PPB, smem, s, (const __half*)x->ptr, x->ld, HW, C8, PPB, groups, ppb, part);
+  else launch_k(gn_stats_kernel, grid, 256, smem, s, tv(*x), HW, groups, ppb, part);
   S2M2_LAUNCH_OK("gn_stats");
   launch_k(gn_final_kernel, cdiv((long long)x->N * groups * 32, 128), 128, 0, s, part, nblk, groups, x->N, (double)HW * (x->C / groups),
                                                                            (float2*)stats);
   S2M2_LAUNCH_OK("gn_final");
+  if (h8) {
+    const int bpi = cdiv(HW, PPB * 8);   // ~8 pixels per thread
+    launch_k(gn_apply_h8_kernel, dim3(bpi < 148 * 8 ? bpi : 148 * 8, x->N), C8 * PPB, 0, s, (const __half*)x->ptr, x->ld, (__half*)y->ptr, y->ld,
+             HW, C8, PPB, groups, (const float2*)stats, gamma, beta);
+    S2M2_LAUNCH_OK("gn_apply_h8");
+    return 0;
+  }
   long long total4 = npix(*x) * (x->C / 4);
   launch_k(gn_apply_kernel, grid_for(total4), 256, 0, s, tv(*x), tv(*y), HW, groups, (const float2*)stats, gamma, beta, total4);
   S2M2_LAUNCH_OK("gn_apply");
@@ -420,6 +570,14 @@ int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
   S2M2_CHECK(x->C == y->C && y->H == x->H / 2 && y->W == x->W / 2 && x->N == y->N && x->H % 2 == 0 && x->W % 2 == 0,
              "avgpool2: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "avgpool2: needs C,ld multiples of 4 and aligned bases");
+  if (h8_ok(*x) && h8_ok(*y)) {
+    const int C8 = x->C / 8, PPB = C8 >= 256 ? 1 : 256 / C8;
+    const int rows = y->N * y->H;
+    launch_k(avgpool2_h8_kernel, rows < 148 * 16 ? rows : 148 * 16, C8 * PPB, 0, (cudaStream_t)stream, (const __half*)x->ptr, x->ld,
+             (__half*)y->ptr, y->ld, x->N, x->H, x->W, C8, PPB);
+    S2M2_LAUNCH_OK("avgpool2_h8");
+    return 0;
+  }
   long long total4 = npix(*y) * (y->C / 4);
   launch_k(avgpool2_kernel, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*x), tv(*y), x->N, x->H, x->W, total4);
   S2M2_LAUNCH_OK("avgpool2");
@@ -429,6 +587,14 @@ int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
 int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
   S2M2_CHECK(x->C == y->C && y->H == x->H * 2 && y->W == x->W * 2 && x->N == y->N, "upsample2x: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "upsample2x: needs C,ld multiples of 4 and aligned bases");
+  if (h8_ok(*x) && h8_ok(*y)) {
+    const int C8 = x->C / 8, PPB = C8 >= 256 ? 1 : 256 / C8;
+    const int rows = y->N * y->H;
+    launch_k(upsample2x_h8_kernel, rows < 148 * 16 ? rows : 148 * 16, C8 * PPB, 0, (cudaStream_t)stream, (const __half*)x->ptr, x->ld,
+             (__half*)y->ptr, y->ld, x->N, x->H, x->W, C8, PPB);
+    S2M2_LAUNCH_OK("upsample2x_h8");
+    return 0;
+  }
   long long total4 = npix(*y) * (y->C / 4);
   launch_k(upsample2x_kernel, grid_for(total4), 256, 0, (cudaStream_t)stream, tv(*x), tv(*y), x->N, x->H, x->W, total4);
   S2M2_LAUNCH_OK("upsample2x");
@@ -500,11 +666,16 @@ int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_
 
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
-  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C >= 16 && vec4_ok(*out),
+  // two output layouts: (2B,H,W,>=16) pixel-major, or (2B,H/2,W/2,64) fp16 space-to-depth (2x2 pixel blocks in the channel dim),
+  // which turns the following 5x5 stride-2 convolution into a dense 3x3 stride-1 one over 64 channels
+  const int s2d = (out->H == H / 2 && out->W == W / 2 && out->C == 64 && H % 2 == 0 && W % 2 == 0) ? 1 : 0;
+  if (s2d) S2M2_CHECK(out->N == 2 * B && out->dtype == S2M2_F16 && out->ld % 8 == 0 && aligned(out->ptr, 16),
+                      "stem: the space-to-depth output must be (2B,H/2,W/2,64) fp16 with 16-byte aligned pixels");
+  else S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C >= 16 && vec4_ok(*out),
              "stem: output must be (2B,H,W,>=16), 4-aligned (channels beyond 16 are zero-filled)");
   StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
   memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
-  launch_k(stem_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, hw, tv(*out));
+  launch_k(stem_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, hw, tv(*out), s2d);
   S2M2_LAUNCH_OK("stem");
   return 0;
 }

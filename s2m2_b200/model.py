@@ -125,6 +125,25 @@ class S2M2(nn.Module):
         bb = None if b is None else b.detach().float().contiguous()
         return ConvW(wp, bb, kh, kw, stride, ph, pw, cin, cout, shuffle, name)
 
+    def _pack_d0(self, name):
+        """conv1_down.0 = Conv2d(16, 64, 5, stride 2, pad 2) (submodules.py:74).  fp32: as is.  fp16: the stem writes its 16
+        channels in space-to-depth layout (2x2 pixel blocks -> 64 channels at half resolution), which turns this layer into
+        a dense 3x3 stride-1 pad-1 convolution over 64 channels (K = 576) for the tcgen05 kernel:
+        W'[co, (py*2+px)*16 + c, ty, tx] = W[co, c, 2*ty + py, 2*tx + px]   (taps with 2*t + p == 5 are zero)."""
+        w, b = self._w(name + ".weight"), self._w(name + ".bias")
+        if self.precision != "fp16":
+            return self._mk(w, b, stride=2, name=name)
+        w3 = w.new_zeros(w.shape[0], 64, 3, 3)
+        for ty in range(3):
+            for py in range(2):
+                for tx in range(3):
+                    for px in range(2):
+                        ky, kx = 2 * ty + py, 2 * tx + px
+                        if ky < 5 and kx < 5:
+                            c0 = (py * 2 + px) * 16
+                            w3[:, c0:c0 + 16, ty, tx] = w[:, :, ky, kx]
+        return self._mk(w3, b, stride=1, name=name)
+
     def _conv(self, name, stride=1, **kw):
         b = self._w(name + ".bias") if self._has(name + ".bias") else None
         return self._mk(self._w(name + ".weight"), b, stride=stride, name=name, **kw)
@@ -244,8 +263,7 @@ class S2M2(nn.Module):
         hostc = lambda t: t.detach().float().cpu().contiguous()      # tiny weights that travel as kernel parameters
         P["bb"] = {"w0": hostc(self._w(f"{b}.conv0.0.weight").reshape(16, 3)), "b0": hostc(self._w(f"{b}.conv0.0.bias")),
                    "w1": hostc(self._w(f"{b}.conv0.2.weight").reshape(16, 16)), "b1": hostc(self._w(f"{b}.conv0.2.bias")),
-                   # fp16: the 16 stem channels are zero-padded to 64 so the 5x5 stride-2 conv runs on the tcgen05 kernel
-                   "d0": self._conv(f"{b}.conv1_down.0", stride=2, cin_to=64 if self.precision == "fp16" else None),
+                   "d0": self._pack_d0(f"{b}.conv1_down.0"),
                    "d2": self._conv(f"{b}.conv1_down.2"),
                    "gn_w": self._w(f"{b}.norm1.weight").float().contiguous(),
                    "gn_b": self._w(f"{b}.norm1.bias").float().contiguous(),
@@ -466,7 +484,8 @@ class S2M2(nn.Module):
 
         # -- CNN backbone (submodules.py:88-93)
         bb = P["bb"]
-        x = ops.empty((2 * B, H, W, bb["d0"].cin), adt, dev)
+        # fp16: space-to-depth stem output (2B,H/2,W/2,64), see _pack_d0; fp32: (2B,H,W,16)
+        x = ops.empty((2 * B, H // 2, W // 2, 64) if self.precision == "fp16" else (2 * B, H, W, 16), adt, dev)
         ops.stem(img0.float().contiguous(), img1.float().contiguous(), bb["w0"], bb["b0"], bb["w1"], bb["b1"], x)
         x = self._c(self._c(x, bb["d0"], ACT_GELU), bb["d2"])
         x2 = self._new(x, C)

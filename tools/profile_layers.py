@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=1216)
     ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("-o", "--out", default=None)
     a = ap.parse_args()
@@ -67,7 +68,7 @@ def main():
     m.my_load_state_dict(random_state_dict(C, NTR, 0))
     m = m.cuda()
     m.ops = TimedOps()
-    left, right = synthetic_pair(1, a.height, a.width, 1)
+    left, right = synthetic_pair(a.batch, a.height, a.width, 1)
     left, right = left.cuda(), right.cuda()
     with torch.no_grad():
         for _ in range(3):
@@ -83,7 +84,7 @@ def main():
         agg[key][0] += 1
         agg[key][1] += e0.elapsed_time(e1) * 1e3
     total = sum(v[1] for v in agg.values())
-    lines = [f"# per-layer device time, {a.model}@{a.width}x{a.height} {a.precision}, one eager forward ({len(m.ops.records)} op calls, "
+    lines = [f"# per-layer device time, {a.model}@{a.width}x{a.height} {a.precision} batch {a.batch}, one eager forward ({len(m.ops.records)} op calls, "
              f"{total / 1e3:.2f} ms summed)", "", "| op:layer | first tensor shape | calls | total us | share | avg us |", "|---|---|---:|---:|---:|---:|"]
     for (label, shape), (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         lines.append(f"| `{label}` | {shape} | {n} | {us:.0f} | {100 * us / total:.1f}% | {us / n:.1f} |")
