@@ -93,6 +93,42 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the pair's TMA loads complete on the LEADER's mbarrier (cluster address with the peer
+// bit cleared), one tcgen05.mma drives both SMs, its commit is multicast to the same barrier offset in both CTAs.
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {   // shared::cluster address of the same offset in CTA rank 0
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+  return remote;
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's copy of a barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -309,10 +345,15 @@ __device__ __forceinline__ float act_fast(float x, int act) {
   }
 }
 
-template <int BN, int STAGES>
+// PAIR: two CTAs of a cluster (one TPC) work on two vertically adjacent 128-pixel tiles with the same output channels as ONE
+// 256 x BN tcgen05.mma.cta_group::2: each CTA loads its own A tile but only half of the weight tile, so the L2->SMEM operand
+// traffic per FLOP (the limiter of the 3x3 convolutions) drops by a third and the ring gets deeper.
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcP p,
                                                                             int m_tiles, int n_tiles) {
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;
+  uint32_t rank = 0;
+  if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -328,7 +369,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
   const int cpb = p.cpb1 + p.cpb2;
   const int nkb = p.taps * cpb;
-  const int total_tiles = m_tiles * n_tiles;
+  // work items: tiles, or (PAIR) pairs of m-tiles (2i, 2i+1) x one n-tile, dealt to CTAs / clusters round-robin
+  const int m_items = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int total_tiles = m_items * n_tiles;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -337,24 +382,32 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4 * TC2_EPI_GROUPS);   // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * a, 4 * TC2_EPI_GROUPS * (PAIR ? 2 : 1));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int a = 0; a < 4 * TC2_EPI_GROUPS; ++a) mbar_init(rbar0 + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   // tile id -> coordinates (n-tile major: tile = nt * m_tiles + mt)
-  auto tile_coords = [&](int tile, int& n0, int& img, int& x0, int& y0) {
-    const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+  auto tile_coords = [&](int tile, int& n0, int& img, int& x0, int& y0) -> bool {
+    const int nt = tile / m_items;
+    int mt = tile - nt * m_items;
+    if constexpr (PAIR) mt = 2 * mt + (int)rank;
     n0 = nt * BN;
     img = 0; y0 = 0;
     if (p.flat) {
@@ -367,40 +420,50 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       x0 = txi * p.tw;
       y0 = tyi * p.th;
     }
+    return mt < m_tiles;   // PAIR, odd tile count: the last pair's second tile lies outside the tensor (TMA zero-fills / clips)
   };
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;  // running k-block counter across tiles
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load_a = [&](const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if constexpr (PAIR) tma_load_4d_pair(m, dst, bar, c0, c1, c2, c3);
+        else tma_load_4d(m, dst, bar, c0, c1, c2, c3);
+      };
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int n0, img, x0, y0;
         tile_coords(tile, n0, img, x0, y0);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+          mbar_wait(empty0 + 8 * s, ph ^ 1);                       // own slot free (the commit is multicast to both CTAs)
+          if constexpr (PAIR) {
+            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + B_BYTES));   // leader's barrier counts both CTAs' bytes
+          } else {
+            mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+          }
           const int tap = kb / cpb, ch = kb - tap * cpb;
           const int ky = tap / p.KW, kx = tap - ky * p.KW;
           const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + s * B_BYTES);
           const int dx = kx - p.pw, dy = ky - p.ph;
           if (p.stride == 1) {
-            if (ch < p.cpb1) tma_load_4d(&maps.act[0], dstA, full0 + 8 * s, ch * TC_BK, x0 + dx, y0 + dy, img);
-            else tma_load_4d(&maps.act[1], dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + dx, y0 + dy, img);
+            if (ch < p.cpb1) load_a(&maps.act[0], dstA, full0 + 8 * s, ch * TC_BK, x0 + dx, y0 + dy, img);
+            else load_a(&maps.act[1], dstA, full0 + 8 * s, (ch - p.cpb1) * TC_BK, x0 + dx, y0 + dy, img);
           } else {
-            tma_load_4d(&maps.act[(dy & 1) * 2 + (dx & 1)], dstA, full0 + 8 * s, ch * TC_BK, x0 + (dx >> 1), y0 + (dy >> 1), img);
+            load_a(&maps.act[(dy & 1) * 2 + (dx & 1)], dstA, full0 + 8 * s, ch * TC_BK, x0 + (dx >> 1), y0 + (dy >> 1), img);
           }
-          tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
+          if constexpr (PAIR) tma_load_2d_pair(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0 + (int)rank * (BN / 2));   // this CTA's half of the weight rows
+          else tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (lane == 0 && rank == 0) {   // PAIR: the leader issues for both SMs
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       uint32_t it = 0, lt = 0;  // k-block counter, local tile counter
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++lt) {
         const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);          // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -412,10 +475,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t ad = make_sdesc(smem_u32(sA + s * A_BYTES)), bd = make_sdesc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(empty0 + 8 * s);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            if constexpr (PAIR) umma_f16_pair(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (PAIR) umma_commit_pair(empty0 + 8 * s);
+          else umma_commit(empty0 + 8 * s);
         }
-        umma_commit(tfull0 + 8 * acc);
+        if constexpr (PAIR) umma_commit_pair(tfull0 + 8 * acc);
+        else umma_commit(tfull0 + 8 * acc);
       }
     }
   } else {
@@ -430,14 +498,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
     uint8_t* stg = sStage + (warp - 2) * STG_STRIDE;
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t lt = 0, rt = 0;   // tiles processed, residual tiles loaded (phase of this warp's residual barrier)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++lt) {
       int n0, img, x0, y0;
-      tile_coords(tile, n0, img, x0, y0);
+      const bool tile_ok = tile_coords(tile, n0, img, x0, y0);
       const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
       bool valid;
       long long opix;
       int py = 0, px = 0;
-      if (p.flat) {
+      if (!tile_ok) {
+        valid = false; opix = 0;
+      } else if (p.flat) {
         valid = x0 + r < p.Wo;
         opix = x0 + r;
       } else {
@@ -479,7 +549,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       if (p.tma_store) {   // the previous tile's bulk store must have read the staging tile before it is overwritten
         if (lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (p.tma_res && n0 + half * CG < p.Cout) {   // residual tile (same box as the store) -> staging buffer
+          if (p.tma_res && tile_ok && n0 + half * CG < p.Cout) {   // residual tile (same box as the store) -> staging buffer
             const int r0 = q * 32;
             int cx, cy;
             if (p.flat) { cx = x0 + r0; cy = 0; }
@@ -493,7 +563,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      if (p.tma_res && n0 + half * CG < p.Cout) {
+      const bool use_tma_res = p.tma_res && tile_ok;
+      if (use_tma_res && n0 + half * CG < p.Cout) {
         mbar_wait(rbar0 + 8 * (warp - 2), rt & 1);
         ++rt;
       }
@@ -548,7 +619,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           off = pix * p.y_ld + co;
         } else {
           off = opix * p.y_ld + n;
-          if (p.tma_res) {
+          if (use_tma_res) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const uint32_t lin = (uint32_t)lane * (CG * 2) + (uint32_t)(c * 2 + u) * 16;
@@ -620,8 +691,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       if (p.tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
-        if (p.tma_store && n0 + half * CG < p.Cout && !(p.dbg & 3)) {
+        if constexpr (PAIR) mbar_arrive_leader(tempty0 + 8 * acc);   // the leader's MMA thread waits for both CTAs' epilogues
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+        if (p.tma_store && tile_ok && n0 + half * CG < p.Cout && !(p.dbg & 3)) {
           // one bulk tensor store: 32 pixels (rows q*32.. of the tile) x CG channels; TMA clips everything outside the tensor
           const int r0 = q * 32;
           int cx, cy;
@@ -636,10 +708,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
   }
 }
 
@@ -741,24 +815,43 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles, cudaStream_t s) {
   constexpr size_t stg = 4 * TC2_EPI_GROUPS * 1024 * ((32 * (BN / TC2_EPI_GROUPS) * 2 + 1023) / 1024);
-  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + stg + (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS) * 8 + 16 + 1024;
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + (PAIR ? BN / 2 : BN) * TC_BK * 2) + stg + (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     attr = true;
   }
+  if constexpr (PAIR) {   // clusters of two CTAs (one TPC); one cluster per pair of m-tiles
+    const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles;
+    const int clusters = (int)(pairs < sms / 2 ? pairs : sms / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(TC2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, STAGES, PAIR>, maps, p, m_tiles, n_tiles);
+    S2M2_LAUNCH_OK("conv_tc_pair");
+    return 0;
+  }
   const long long tiles = (long long)m_tiles * n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  launch_k(conv_tc_persistent_kernel<BN, STAGES>, grid, TC2_THREADS, smem, s, maps, p, m_tiles, n_tiles);
+  launch_k(conv_tc_persistent_kernel<BN, STAGES, PAIR>, grid, TC2_THREADS, smem, s, maps, p, m_tiles, n_tiles);
   S2M2_LAUNCH_OK("conv_tc_persistent");
   return 0;
 }
@@ -810,16 +903,22 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   // problems (1/16, 1/32 resolution) take narrower tiles so that ~every SM gets one.
   int BN = a->Cout >= 256 ? 256 : (a->Cout >= 128 ? 128 : 64);
   while (BN > 64 && mtiles * cdiv(a->Cout, BN) < 120) BN /= 2;
+  static const int use_v1 = getenv("S2M2_TC_V1") ? atoi(getenv("S2M2_TC_V1")) : 0;
+  // CTA pairs (cta_group::2) for the wide tiles of the deep-K layers (3x3, 3x1/1x3, 5x5: +4..10 % measured) once there is work
+  // for every TPC; the K <= 512 linears are epilogue-bound and lose to the pair's extra synchronisation.  S2M2_TC_PAIR=0: off,
+  // =2: every BN = 256 layer.
+  static const int pair_env = getenv("S2M2_TC_PAIR") ? atoi(getenv("S2M2_TC_PAIR")) : 1;
+  const long long nkb_host = (long long)p.taps * (p.cpb1 + p.cpb2);
+  const bool pair = pair_env && !use_v1 && BN == 256 && mtiles * cdiv(a->Cout, BN) >= 296 && (nkb_host >= 16 || pair_env == 2);
   {
     const long long K = (long long)p.taps * (x.C + (x2.ptr ? x2.C : 0));
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Cout}, strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)(pair ? BN / 2 : BN)}, estr[2] = {1, 1};   // a pair's CTA loads half of the rows
     CUresult r = get_encode()(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     S2M2_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
-  static const int use_v1 = getenv("S2M2_TC_V1") ? atoi(getenv("S2M2_TC_V1")) : 0;
   static const int dbg = getenv("S2M2_TC_DBG") ? atoi(getenv("S2M2_TC_DBG")) : 0;
   p.dbg = dbg;
   if (!use_v1) {
@@ -858,6 +957,7 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
       maps.out = maps.w;
       maps.res = maps.w;
     }
+    if (pair) return launch_tc2<256, 5, true>(maps, p, (int)mtiles, nt, s);
     if (BN == 256) return launch_tc2<256, 3>(maps, p, (int)mtiles, nt, s);
     if (BN == 128) return launch_tc2<128, 5>(maps, p, (int)mtiles, nt, s);
     return launch_tc2<64, 8>(maps, p, (int)mtiles, nt, s);

@@ -30,6 +30,12 @@ CASES = [
     (2, 24, 36, 128, 0, 128, 3, 3, ACT_NONE, False, False, False, 0, 2),  # 3x3 stride 2 (conv2_down) via parity views
     (1, 64, 76, 256, 0, 256, 3, 3, ACT_GELU, False, False, False, 0, 2),  # 3x3 stride 2, N=256
     (2, 48, 72, 64, 0, 64, 5, 5, ACT_GELU, False, False, False, 0, 2),    # 5x5 stride 2 (conv1_down.0 with padded channels)
+    # CTA-pair (cta_group::2) path: BN = 256, >= 296 tiles, K >= 1024
+    (2, 152, 127, 64, 0, 256, 3, 3, ACT_GELU, True, False, False, 0),     # 3x3 + residual, ragged patches, odd number of m-tiles
+    (1, 1, 39001, 1024, 0, 768, 1, 1, ACT_NONE, False, False, False, 0),  # flat 1x1, ragged M, 3 n-tiles, odd number of m-tiles
+    (1, 160, 250, 512, 512, 384, 1, 1, ACT_GELU, False, False, False, 0), # two-source 1x1, Cout 384 (second n-tile half empty)
+    (2, 300, 260, 64, 0, 256, 3, 3, ACT_RELU, False, False, False, 0, 2), # 3x3 stride 2 through the parity views
+    (1, 200, 200, 128, 0, 256, 3, 1, ACT_TANH, True, False, True, 0),     # GRU 3x1, fp32 output (no TMA store), residual loads
 ]
 
 

@@ -164,6 +164,17 @@ def test_l_1216x1024_headline_config_vs_oracle_on_gpu():
         assert err.mean().item() < tol           # north_star: EPE < 1e-3 px vs the fp32 reference
         if prec == "fp32":
             assert flips == 0
+        if prec == "fp16":
+            # BASELINE config 5's per-GPU share is a batch of pairs: pair 0 of a batch (with a different second pair) must
+            # reproduce the single-pair result at the headline size (pairs are independent units)
+            l2, r2 = synthetic_pair(1, 1024, 1216, 7)
+            ob = [t.cpu() for t in m(torch.cat([left, l2]).to(DEV), torch.cat([right, r2]).to(DEV))]
+            eb = (ob[0][0] - ref[0][0]).abs()
+            db = (ob[0][0] - out[0][0]).abs()
+            print(f"L 1216x1024 fp16 batch 2, pair 0: EPE vs oracle {eb.mean().item():.3e}, vs single-pair call {db.mean().item():.3e} "
+                  f"max {db.max().item():.3e}")
+            assert eb.mean().item() < tol and db.mean().item() < 1e-4
+            assert not torch.equal(ob[0][1], ob[0][0])               # the second pair is a different problem
         del m
         torch.cuda.empty_cache()
 
