@@ -194,10 +194,10 @@ using namespace s2m2;
 extern "C" int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, int32_t d, int32_t dtype) {
   AttnP p{};
   p.S = S; p.N = N; p.heads = heads; p.d = d; p.C = heads * d; p.qh = p.oh = (dtype == S2M2_F16);
-  static int dummy_aligned[4];
+  alignas(16) static int dummy_aligned[4];
   p.qkv = dummy_aligned; p.out = dummy_aligned;   // alignment checks are on the real pointers at launch time
   p.qkv_ld = 3 * p.C; p.out_ld = p.C;
-  if (!p.qh || !(d == 64 || d == 128 || d == 256) || N < 48 || N > 384) return 0;
+  if (!attention_tc_supported(p)) return 0;
   return (int64_t)attention_tc_workspace_bytes(p);
 }
 

@@ -142,6 +142,9 @@ ATTN_CASES = [
     (4, 80, 2, 64, False, None),        # S level 1
     (2, 384, 1, 64, False, None),       # longest row the whole-row kernel takes
     (2, 100, 1, 384, True, None),       # XL level 0 head dim (value channels split over two CTAs)
+    (4, 32 * 38, 8, 64, True, None),    # L@1216x1024 2-D global cross attention at 1/32 (mma.sync flash kernel, 19 key tiles)
+    (2, 1000, 2, 64, False, None),      # ragged query and key tiles
+    (2, 385, 1, 64, False, None),       # just above the whole-row kernel's limit
 ]
 
 

@@ -13,7 +13,10 @@ from s2m2_b200.ops import CudaOps  # noqa: E402
 SHAPES = [("1/4  scan-line",    512, 304, 1,    256, True),
           ("1/8  scan-line",    256, 152, 2,    128, True),
           ("1/16 scan-line",    128, 76,  4,    128, True),
-          ("1/32 global 2-D",   2,   1216, 8,   64,  True)]
+          ("1/32 global 2-D",   2,   1216, 8,   64,  True),
+          ("1/32 2-D batch 2",  4,   1216, 8,   64,  True),
+          ("1/32 2-D batch 4",  8,   1216, 8,   64,  True),
+          ("1/32 2-D batch 8",  16,  1216, 8,   64,  True)]
 
 
 def timeit(fn, reps=20):
