@@ -99,6 +99,27 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
+// activation for fp16 outputs: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below fp16 rounding) and exp-based
+// sigmoid / tanh; the fp32 parity mode keeps act_apply() above
+__device__ __forceinline__ float act_apply_fast(float x, int act) {
+  switch (act) {
+    case S2M2_ACT_GELU: {
+      const float z = x * 0.70710678118654752440f, az = fabsf(z);
+      const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+      float poly = fmaf(1.061405429f, t, -1.453152027f);
+      poly = fmaf(poly, t, 1.421413741f);
+      poly = fmaf(poly, t, -0.284496736f);
+      poly = fmaf(poly, t, 0.254829592f);
+      const float e = copysignf(1.0f - poly * t * __expf(-az * az), z);
+      return 0.5f * x * (1.0f + e);
+    }
+    case S2M2_ACT_RELU: return fmaxf(x, 0.0f);
+    case S2M2_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
+    case S2M2_ACT_TANH: return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+    default: return x;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

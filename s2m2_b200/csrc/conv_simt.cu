@@ -262,39 +262,62 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) conv_simt_kernel(Con
 // The tiled GEMM above wastes its K loop on them; here a thread gathers its pixel's K inputs once and produces 8
 // output channels from weights held in shared memory; 8-channel groups of one pixel are adjacent threads (coalesced).
 constexpr int SMALLK_MAX = 32;
+// VEC: fp16 output with 16-byte aligned 8-channel groups -> a thread owns 8 CONSECUTIVE channels (two LDS.128 of weights per k,
+// one 16-byte store, exp-based activation); otherwise channels g, g+NG, .. with scalar stores (any dtype / alignment).
+template <bool VEC>
 __global__ void __launch_bounds__(256) conv_smallk_kernel(ConvP p) {
   pdl_sync();
-  extern __shared__ float sw[];                  // [K][Cout] weights (transposed: lanes read consecutive channels) then [Cout] bias
+  extern __shared__ float sw[];                  // [K][Cout] weights (transposed), [Cout] bias, [K] tap table
   float* sb = sw + p.Cout * p.K;
+  int* stab = (int*)(sb + p.Cout);               // per k: (dy + 128) << 16 | (dx + 128) << 8 | ci
   for (int i = threadIdx.x; i < p.Cout * p.K; i += blockDim.x) {
     const int co = i / p.K, k = i - co * p.K;
     sw[k * p.Cout + co] = ld1(p.w, i, p.wh);
   }
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias ? p.bias[i] : 0.f;
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+    const int tap = k / p.Cin, ci = k - tap * p.Cin;
+    const int ky = tap / p.KW, kx = tap - ky * p.KW;
+    stab[k] = ((ky - p.ph + 128) << 16) | ((kx - p.pw + 128) << 8) | ci;
+  }
   __syncthreads();
-  const int NG = p.Cout >> 3;                    // threads per pixel; thread g owns channels g, g+NG, ..., g+7*NG
+  const int NG = p.Cout >> 3;                    // threads per pixel
   const long long total = (long long)p.M * NG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / NG), g = (int)(i - (long long)m * NG);
     const int ox = m % p.Wo;
     const int t = m / p.Wo;
     const int oy = t % p.Ho, n = t / p.Ho;
+    const int cb = VEC ? 8 * g : g, cs = VEC ? 1 : NG;     // first channel and channel step of this thread
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = sb[g + j * NG];
+    for (int j = 0; j < 8; ++j) o[j] = sb[cb + j * cs];
+    const long long img = (long long)n * p.H;
     for (int k = 0; k < p.K; ++k) {
-      const int tap = k / p.Cin, ci = k - tap * p.Cin;
-      const int ky = tap / p.KW, kx = tap - ky * p.KW;
-      const int iy = oy * p.stride - p.ph + ky, ix = ox * p.stride - p.pw + kx;
+      const int e = stab[k];
+      const int iy = oy * p.stride + (e >> 16) - 128, ix = ox * p.stride + ((e >> 8) & 255) - 128;
       float a = 0.f;
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) a = ld1(p.x, (((long long)n * p.H + iy) * p.W + ix) * p.x_ld + ci, p.xh);
-      const float* wr = sw + k * p.Cout + g;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) a = ld1(p.x, ((img + iy) * p.W + ix) * p.x_ld + (e & 255), p.xh);
+      if constexpr (VEC) {
+        const float4 w0 = *(const float4*)(sw + k * p.Cout + cb), w1 = *(const float4*)(sw + k * p.Cout + cb + 4);
+        o[0] = fmaf(a, w0.x, o[0]); o[1] = fmaf(a, w0.y, o[1]); o[2] = fmaf(a, w0.z, o[2]); o[3] = fmaf(a, w0.w, o[3]);
+        o[4] = fmaf(a, w1.x, o[4]); o[5] = fmaf(a, w1.y, o[5]); o[6] = fmaf(a, w1.z, o[6]); o[7] = fmaf(a, w1.w, o[7]);
+      } else {
+        const float* wr = sw + k * p.Cout + g;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(a, wr[j * NG], o[j]);
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(a, wr[j * NG], o[j]);
+      }
     }
-    const long long off = (long long)m * p.y_ld + g;
+    if constexpr (VEC) {
+      __half2 h[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) st1(p.y, off + j * NG, p.yh, act_apply(o[j], p.act));
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(act_apply_fast(o[2 * j], p.act), act_apply_fast(o[2 * j + 1], p.act));
+      *(uint4*)((__half*)p.y + (long long)m * p.y_ld + cb) = *(uint4*)h;
+    } else {
+      const long long off = (long long)m * p.y_ld + g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st1(p.y, off + j * NG, p.yh, act_apply(o[j], p.act));
+    }
   }
 }
 
@@ -335,8 +358,10 @@ int conv_simt_launch(const S2m2Conv* a, cudaStream_t s) {
     const long long total = (long long)p.M * (p.Cout / 8);
     long long g = (total + 255) / 256;
     if (g > 148LL * 32) g = 148LL * 32;
-    const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout);
-    launch_k(conv_smallk_kernel, (int)g, 256, smem, s, p);
+    const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout + p.K);
+    const bool v8 = p.yh && p.y_ld % 8 == 0 && aligned(y.ptr, 16) && p.Cin < 256 && p.KH <= 128 && p.KW <= 128;
+    if (v8) launch_k(conv_smallk_kernel<true>, (int)g, 256, smem, s, p);
+    else launch_k(conv_smallk_kernel<false>, (int)g, 256, smem, s, p);
     S2M2_LAUNCH_OK("conv_smallk");
     return 0;
   }
