@@ -121,9 +121,11 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W,
                         const S2m2Tensor* out, void* stream);
 
-/* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images -> (2B,H,W,C>=16; channels
- * beyond 16 are written as zeros so that the 5x5 stride-2 conv that follows can take 64-channel tcgen05 k-blocks)
- * (s2m2.py:86-87, submodules.py:70-72,89).  w0 (16,3), w1 (16,16), biases (16): fp32 HOST pointers (they become kernel parameters). */
+/* Fused stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16) on both NCHW fp32 images (s2m2.py:86-87,
+ * submodules.py:70-72,89).  Two output layouts, chosen by the shape of `out`:
+ *   (2B,H,W,C>=16)      pixel-major, channels beyond 16 written as zeros;
+ *   (2B,H/2,W/2,64) fp16  space-to-depth: channel ((y&1)*2 + (x&1))*16 + c of block (y/2, x/2) — the 5x5 stride-2 conv that
+ *                        follows (submodules.py:74) then is a dense 3x3 stride-1 conv over 64 channels (model._pack_d0).  w0 (16,3), w1 (16,16), biases (16): fp32 HOST pointers (they become kernel parameters). */
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream);
 /* Fused UpsampleMask1x inputs (submodules.py:121-124,138-139): out[...,0:16] = relu(convT3x3(up[...,0])),
