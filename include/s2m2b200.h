@@ -97,6 +97,23 @@ int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void* w0, const
  * runs layernorm + conv2d), < 0 = error. */
 int s2m2b200_ln_linear(const S2m2Tensor* x, const S2m2Tensor* y, const void* w, const float* bias, int32_t w_dtype, void* stream);
 
+/* ---- the callers either side of the forward ---- */
+/* uint8 ingest (§8(f)1): same as s2m2b200_preprocess / s2m2b200_stem but the NCHW images are uint8 (4x fewer input bytes; the
+ * reference converts to float on the host, model_utils.py:72-73 after image_utils.py:20-21).  Bit-identical results. */
+int s2m2b200_preprocess_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
+                           void* stream);
+int s2m2b200_stem_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
+                     const float* w1, const float* b1, const S2m2Tensor* out, void* stream);
+/* Batched confidence score (§8(f)2; model_utils.py:93-94 after image_crop, image_utils.py:66-96): out[b] = mean of conf[b] over
+ * the centre crop (crop_h, crop_w) shrunk by `margin` on every side.  conf: (B,H,W) fp32; out: B floats (device). */
+int s2m2b200_confidence_score(const float* conf, int32_t B, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w, int32_t margin,
+                              float* out, void* stream);
+/* Disparity -> camera-frame points (§8(f)3; model_utils.py:111-136 with open3d's RGBD back-projection, trust mask of
+ * vis_utils.py:62).  disp/conf/occ: (B,H,W) fp32 (conf, occ may be NULL); xyz: (B,H,W,3) fp32; valid: (B,H,W) bytes. */
+int s2m2b200_disparity_to_points(const float* disp, const float* conf, const float* occ, int32_t B, int32_t H, int32_t W, float fx, float cx,
+                                 float cy, float baseline, float doffs, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
+                                 void* stream);
+
 /* Relative-PE table of utils.py:32-60 for one axis of length n: HOST output (2n+1, 16) floats. */
 int s2m2b200_pe_table(int32_t n, float* host_out);
 

@@ -1,0 +1,49 @@
+"""TEST INFRASTRUCTURE — CPU restatement of the reference's post-processing around the forward.
+
+Only tests/ may import this.  Each function cites the reference lines it follows.
+"""
+import torch
+
+
+def image_crop(img: torch.Tensor, img_shape):
+    """image_utils.py:66-96: centre crop of the last two dims, floor(d/2) dropped in front, the rest behind."""
+    H, W = img.shape[-2:]
+    Hn, Wn = img_shape
+    ch, cw = H - Hn, W - Wn
+    if ch > 0:
+        img = img[..., ch // 2: H - (ch - ch // 2), :]
+    if cw > 0:
+        img = img[..., :, cw // 2: W - (cw - cw // 2)]
+    return img
+
+
+def confidence_score(pred_conf: torch.Tensor, img_hw, margin: int = 100) -> torch.Tensor:
+    """model_utils.py:86-95: crop to the un-padded size, squeeze, ``[margin:-margin, margin:-margin].mean()`` — per pair."""
+    c = image_crop(pred_conf.float(), img_hw)
+    if c.dim() == 4:
+        c = c[:, 0]
+    return c[:, margin:-margin, margin:-margin].double().mean(dim=(1, 2)).float()
+
+
+def disparity_to_points(disp, fx, cx, cy, baseline, doffs=0.0, conf=None, occ=None, depth_scale=1000.0, depth_trunc=1e9):
+    """model_utils.py:111-136 (depth = baseline*fx/(disp+doffs), depth[disp<=0] = 1e9) followed by what open3d's
+    ``RGBDImage.create_from_color_and_depth`` / ``create_from_rgbd_image`` do with it: z = depth/depth_scale, depths beyond
+    ``depth_trunc`` dropped, x = (u-cx) z/fx, y = (v-cy) z/fy (fy = fx here).  Trust mask: vis_utils.py:62."""
+    d = disp.float()
+    if d.dim() == 4:
+        d = d[:, 0]
+    B, H, W = d.shape
+    depth = baseline * fx / (d + doffs)
+    depth = torch.where(d <= 0, torch.full_like(depth, 1e9), depth)
+    z = depth / depth_scale
+    ok = (z > 0) & (z <= depth_trunc)
+    z = torch.where(ok, z, torch.zeros_like(z))
+    u = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    v = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    xyz = torch.stack([(u - cx) * z / fx, (v - cy) * z / fx, z], dim=-1)
+    valid = ok
+    if conf is not None:
+        valid = valid & (conf.float().reshape(B, H, W) > 0.1)
+    if occ is not None:
+        valid = valid & (occ.float().reshape(B, H, W) > 0.5)
+    return xyz, valid

@@ -358,14 +358,17 @@ __global__ void ew_kernel(TV a, TV b, TV c, TV d, TV o, int act, long long total
   }
 }
 
-__global__ void preprocess_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W, TV o) {
+// TIn = float (what image_pad hands to the model, model_utils.py:72-73) or uint8_t (4x fewer input bytes; the
+// values are the same integers, so both instantiations produce bit-identical results)
+template <typename TIn>
+__global__ void preprocess_kernel(const TIn* __restrict__ left, const TIn* __restrict__ right, int B, int H, int W, TV o) {
   pdl_sync();
   const long long HW = (long long)H * W, total = 2LL * B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long n = i / HW, hw = i - n * HW;
-    const float* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
+    const TIn* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) st1(o.p, i * o.ld + c, o.half, (src[c * HW + hw] / 255.f - 0.5f) * 2.f);
+    for (int c = 0; c < 3; ++c) st1(o.p, i * o.ld + c, o.half, ((float)src[c * HW + hw] / 255.f - 0.5f) * 2.f);
   }
 }
 
@@ -375,17 +378,18 @@ __global__ void preprocess_kernel(const float* __restrict__ left, const float* _
 // ------------------------------------------------------------------------------------------------
 // stem: normalise -> Conv1x1(3->16) -> GELU -> Conv1x1(16->16)   (s2m2.py:86-87, submodules.py:70-72)
 struct StemW { float w0[48], b0[16], w1[256], b1[16]; };      // passed by value: constant bank, warp-uniform reads
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ left, const float* __restrict__ right, int B, int H, int W,
+template <typename TIn>
+__global__ void __launch_bounds__(256) stem_kernel(const TIn* __restrict__ left, const TIn* __restrict__ right, int B, int H, int W,
                                                    const __grid_constant__ StemW wts, TV o, int s2d) {
   pdl_sync();
   const float* sw0 = wts.w0; const float* sb0 = wts.b0; const float* sw1 = wts.w1; const float* sb1 = wts.b1;
   const long long HW = (long long)H * W, total = 2LL * B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long n = i / HW, hw = i - n * HW;
-    const float* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
+    const TIn* src = n < B ? left + n * 3 * HW : right + (n - B) * 3 * HW;
     float x[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) x[c] = (src[c * HW + hw] / 255.f - 0.5f) * 2.f;
+    for (int c = 0; c < 3; ++c) x[c] = ((float)src[c * HW + hw] / 255.f - 0.5f) * 2.f;
     float hdn[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -514,6 +518,31 @@ using namespace s2m2;
 // ==================================================================================================
 // C-ABI
 // ==================================================================================================
+template <typename TIn>
+static int preprocess_any(const TIn* left, const TIn* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out, void* stream) {
+  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 3, "preprocess: output must be (2B,H,W,3)");
+  launch_k(preprocess_kernel<TIn>, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, tv(*out));
+  S2M2_LAUNCH_OK("preprocess");
+  return 0;
+}
+
+template <typename TIn>
+static int stem_any(const TIn* left, const TIn* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
+                    const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
+  // two output layouts: (2B,H,W,>=16) pixel-major, or (2B,H/2,W/2,64) fp16 space-to-depth (2x2 pixel blocks in the channel dim),
+  // which turns the following 5x5 stride-2 convolution into a dense 3x3 stride-1 one over 64 channels
+  const int s2d = (out->H == H / 2 && out->W == W / 2 && out->C == 64 && H % 2 == 0 && W % 2 == 0) ? 1 : 0;
+  if (s2d) S2M2_CHECK(out->N == 2 * B && out->dtype == S2M2_F16 && out->ld % 8 == 0 && aligned(out->ptr, 16),
+                      "stem: the space-to-depth output must be (2B,H/2,W/2,64) fp16 with 16-byte aligned pixels");
+  else S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C >= 16 && vec4_ok(*out),
+             "stem: output must be (2B,H,W,>=16), 4-aligned (channels beyond 16 are zero-filled)");
+  StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
+  memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
+  launch_k(stem_kernel<TIn>, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, hw, tv(*out), s2d);
+  S2M2_LAUNCH_OK("stem");
+  return 0;
+}
+
 extern "C" {
 
 int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* gamma, const float* beta, void* stream) {
@@ -658,26 +687,20 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
                         void* stream) {
-  S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C == 3, "preprocess: output must be (2B,H,W,3)");
-  launch_k(preprocess_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, tv(*out));
-  S2M2_LAUNCH_OK("preprocess");
-  return 0;
+  return preprocess_any(left, right, B, H, W, out, stream);
+}
+int s2m2b200_preprocess_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
+                           void* stream) {
+  return preprocess_any(left, right, B, H, W, out, stream);
 }
 
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
-  // two output layouts: (2B,H,W,>=16) pixel-major, or (2B,H/2,W/2,64) fp16 space-to-depth (2x2 pixel blocks in the channel dim),
-  // which turns the following 5x5 stride-2 convolution into a dense 3x3 stride-1 one over 64 channels
-  const int s2d = (out->H == H / 2 && out->W == W / 2 && out->C == 64 && H % 2 == 0 && W % 2 == 0) ? 1 : 0;
-  if (s2d) S2M2_CHECK(out->N == 2 * B && out->dtype == S2M2_F16 && out->ld % 8 == 0 && aligned(out->ptr, 16),
-                      "stem: the space-to-depth output must be (2B,H/2,W/2,64) fp16 with 16-byte aligned pixels");
-  else S2M2_CHECK(out->N == 2 * B && out->H == H && out->W == W && out->C >= 16 && vec4_ok(*out),
-             "stem: output must be (2B,H,W,>=16), 4-aligned (channels beyond 16 are zero-filled)");
-  StemW hw;   // w0/b0/w1/b1 are HOST pointers: the 1.3 KB of weights travel as a kernel parameter (constant bank)
-  memcpy(hw.w0, w0, sizeof(hw.w0)); memcpy(hw.b0, b0, sizeof(hw.b0)); memcpy(hw.w1, w1, sizeof(hw.w1)); memcpy(hw.b1, b1, sizeof(hw.b1));
-  launch_k(stem_kernel, grid_for(2LL * B * H * W), 256, 0, (cudaStream_t)stream, left, right, B, H, W, hw, tv(*out), s2d);
-  S2M2_LAUNCH_OK("stem");
-  return 0;
+  return stem_any(left, right, B, H, W, w0, b0, w1, b1, out, stream);
+}
+int s2m2b200_stem_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
+                     const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
+  return stem_any(left, right, B, H, W, w0, b0, w1, b1, out, stream);
 }
 
 int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* wd, const float* bd, const float* wr,

@@ -292,6 +292,55 @@ __global__ void filter2x_kernel(const float4* __restrict__ up, const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// consumers of the three output maps, fused so that the maps need not leave the device
+// ------------------------------------------------------------------------------------------------
+// mean confidence over the interior of the centre crop: image_crop (image_utils.py:66-96) to (crop_h, crop_w), then
+// [margin:-margin, margin:-margin].mean() (model_utils.py:93-94).  One CTA per image, fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024) confidence_score_kernel(const float* __restrict__ conf, int H, int W, int y0, int y1, int x0, int x1,
+                                                                float* __restrict__ out) {
+  pdl_sync();
+  __shared__ double sh[1024];
+  const float* img = conf + (long long)blockIdx.x * H * W;
+  const int ww = x1 - x0, n = (y1 - y0) * ww;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int y = y0 + i / ww, x = x0 + i - (i / ww) * ww;
+    acc += (double)img[(long long)y * W + x];
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = n > 0 ? (float)(sh[0] / n) : nanf("");
+}
+
+// disparity -> camera-frame points (model_utils.py:111-136 + open3d's RGBD back-projection): depth = baseline*fx/(disp+doffs),
+// depth[disp<=0] = 1e9, z = depth/depth_scale, dropped if z > depth_trunc; x = (u-cx) z / fx, y = (v-cy) z / fx;
+// trust mask conf > .1 and occ > .5 (vis_utils.py:62).  xyz: (B,H,W,3) fp32, valid: (B,H,W) bytes.
+__global__ void disparity_to_points_kernel(const float* __restrict__ disp, const float* __restrict__ conf, const float* __restrict__ occ,
+                                           long long n, int H, int W, float fx, float cx, float cy, float baseline, float doffs,
+                                           float depth_scale, float depth_trunc, float* __restrict__ xyz, uint8_t* __restrict__ valid) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % W), v = (int)((i / W) % H);
+    const float d = disp[i];
+    float depth = baseline * fx / (d + doffs);
+    if (d <= 0.f) depth = 1e9f;
+    const float z = depth / depth_scale;
+    bool ok = z > 0.f && z <= depth_trunc;
+    if (conf) ok = ok && conf[i] > 0.1f;
+    if (occ) ok = ok && occ[i] > 0.5f;
+    const float zz = (z > 0.f && z <= depth_trunc) ? z : 0.f;
+    xyz[3 * i + 0] = (u - cx) * zz / fx;
+    xyz[3 * i + 1] = (v - cy) * zz / fx;
+    xyz[3 * i + 2] = zz;
+    valid[i] = ok ? 1 : 0;
+  }
+}
 }  // namespace s2m2
 
 using namespace s2m2;
@@ -343,3 +392,26 @@ int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, i
 }
 
 }  // extern "C"
+
+int s2m2b200_confidence_score(const float* conf, int32_t B, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w, int32_t margin,
+                              float* out, void* stream) {
+  S2M2_CHECK(crop_h > 0 && crop_w > 0 && crop_h <= H && crop_w <= W && margin >= 0, "confidence_score: bad crop / margin");
+  const int ys = (H - crop_h) / 2, xs = (W - crop_w) / 2;     // image_crop drops floor(d/2) rows/columns in front
+  const int y0 = ys + margin, y1 = ys + crop_h - margin, x0 = xs + margin, x1 = xs + crop_w - margin;
+  S2M2_CHECK(y1 > y0 && x1 > x0, "confidence_score: the margin leaves no interior");
+  launch_k(confidence_score_kernel, B, 1024, 0, (cudaStream_t)stream, conf, H, W, y0, y1, x0, x1, out);
+  S2M2_LAUNCH_OK("confidence_score");
+  return 0;
+}
+
+int s2m2b200_disparity_to_points(const float* disp, const float* conf, const float* occ, int32_t B, int32_t H, int32_t W, float fx, float cx,
+                                 float cy, float baseline, float doffs, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
+                                 void* stream) {
+  S2M2_CHECK(fx > 0.f && depth_scale > 0.f, "disparity_to_points: fx and depth_scale must be positive");
+  const long long n = (long long)B * H * W;
+  const long long g = (n + 255) / 256;
+  launch_k(disparity_to_points_kernel, (int)(g > 148 * 32 ? 148 * 32 : g), 256, 0, (cudaStream_t)stream, disp, conf, occ, n, H, W, fx, cx, cy,
+           baseline, doffs, depth_scale, depth_trunc, xyz, valid);
+  S2M2_LAUNCH_OK("disparity_to_points");
+  return 0;
+}

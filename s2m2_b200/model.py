@@ -480,13 +480,16 @@ class S2M2(nn.Module):
 
         # -- normalise + NCHW->NHWC; left and right stacked on the batch dim (s2m2.py:86-96)
         img = ops.empty((2 * B, H, W, 3), adt, dev)                      # normalised NHWC copy (mask head input)
-        ops.preprocess(img0.float().contiguous(), img1.float().contiguous(), img)
+        # float32 (what image_pad produces) or uint8 images (4x fewer input bytes, bit-identical results)
+        u8 = img0.dtype == torch.uint8 and img1.dtype == torch.uint8
+        in0, in1 = (img0.contiguous(), img1.contiguous()) if u8 else (img0.float().contiguous(), img1.float().contiguous())
+        ops.preprocess(in0, in1, img)
 
         # -- CNN backbone (submodules.py:88-93)
         bb = P["bb"]
         # fp16: space-to-depth stem output (2B,H/2,W/2,64), see _pack_d0; fp32: (2B,H,W,16)
         x = ops.empty((2 * B, H // 2, W // 2, 64) if self.precision == "fp16" else (2 * B, H, W, 16), adt, dev)
-        ops.stem(img0.float().contiguous(), img1.float().contiguous(), bb["w0"], bb["b0"], bb["w1"], bb["b1"], x)
+        ops.stem(in0, in1, bb["w0"], bb["b0"], bb["w1"], bb["b1"], x)
         x = self._c(self._c(x, bb["d0"], ACT_GELU), bb["d2"])
         x2 = self._new(x, C)
         ops.groupnorm(x, 8, bb["gn_w"], bb["gn_b"], x2)

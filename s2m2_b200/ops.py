@@ -57,6 +57,7 @@ EXPORTS = [
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
     "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_last_error",
+    "s2m2b200_preprocess_u8", "s2m2b200_stem_u8", "s2m2b200_confidence_score", "s2m2b200_disparity_to_points",
     "s2m2b200_version", "s2m2b200_launch_count",
 ]
 
@@ -259,16 +260,18 @@ class CudaOps:
         self._chk(self.lib.s2m2b200_gru_update(*[C.byref(t) for t in ts], self._stream()), "gru_update")
 
     def preprocess(self, left, right, out):
+        """left/right: (B,3,H,W) contiguous, float32 or uint8 (the same integer values either way)."""
         B, _, H, W = left.shape
         ot = tview(out)
-        self._chk(self.lib.s2m2b200_preprocess(C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()), B, H, W,
-                                               C.byref(ot), self._stream()), "preprocess")
+        fn = self.lib.s2m2b200_preprocess_u8 if left.dtype == torch.uint8 else self.lib.s2m2b200_preprocess
+        self._chk(fn(C.c_void_p(left.data_ptr()), C.c_void_p(right.data_ptr()), B, H, W, C.byref(ot), self._stream()), "preprocess")
 
     def stem(self, left, right, w0, b0, w1, b1, out):
         B, _, H, W = left.shape
         ot = tview(out)
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._chk(self.lib.s2m2b200_stem(p(left), p(right), B, H, W, p(w0), p(b0), p(w1), p(b1), C.byref(ot), self._stream()), "stem")
+        fn = self.lib.s2m2b200_stem_u8 if left.dtype == torch.uint8 else self.lib.s2m2b200_stem
+        self._chk(fn(p(left), p(right), B, H, W, p(w0), p(b0), p(w1), p(b1), C.byref(ot), self._stream()), "stem")
 
     def mask1x_inputs(self, up, rgb, wd, bd, wr, br, out):
         rt, ot = tview(rgb), tview(out)
@@ -332,3 +335,18 @@ class CudaOps:
         p = lambda t: C.c_void_p(t.data_ptr())
         self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), logits.shape[3], B, H, W, p(out), int(upsample2), self._stream()),
                   "filter1x")
+
+    # -- consumers of the output maps
+    def confidence_score(self, conf, crop_hw, margin, out):
+        """out[b] = mean of conf[b] over the centre crop `crop_hw` shrunk by `margin` (model_utils.py:93-94)."""
+        B, H, W = conf.shape[0], conf.shape[-2], conf.shape[-1]
+        self._chk(self.lib.s2m2b200_confidence_score(C.c_void_p(conf.data_ptr()), B, H, W, int(crop_hw[0]), int(crop_hw[1]), int(margin),
+                                                     C.c_void_p(out.data_ptr()), self._stream()), "confidence_score")
+
+    def disparity_to_points(self, disp, conf, occ, fx, cx, cy, baseline, doffs, depth_scale, depth_trunc, xyz, valid):
+        B, H, W = disp.shape[0], disp.shape[-2], disp.shape[-1]
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        f = C.c_float
+        self._chk(self.lib.s2m2b200_disparity_to_points(p(disp), p(conf), p(occ), B, H, W, f(fx), f(cx), f(cy), f(baseline), f(doffs),
+                                                        f(depth_scale), f(depth_trunc), p(xyz), p(valid), self._stream()),
+                  "disparity_to_points")

@@ -430,3 +430,43 @@ def test_stem_space_to_depth(ops):
     cu.stem(l, r, w0, b0, w1, b1, c)
     c = c.reshape(2 * B, H // 2, 2, W // 2, 2, 16).permute(0, 1, 3, 2, 4, 5).reshape(2 * B, H // 2, W // 2, 64)
     assert torch.equal(a, c)
+
+
+def test_uint8_ingest_is_bit_identical(ops):
+    """uint8 NCHW images through preprocess / stem give exactly the float-input results."""
+    cu, _ = ops
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 2, 16, 24
+    lu = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    ru = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    cpu = lambda shape, sc: (torch.randn(shape, generator=g) * sc).contiguous()
+    w0, b0, w1, b1 = cpu((16, 3), 0.5), cpu((16,), 0.5), cpu((16, 16), 0.25), cpu((16,), 0.25)
+    for dtype in (torch.float16, torch.float32):
+        a, b = (torch.zeros((2 * B, H, W, 3), dtype=dtype, device=DEV) for _ in range(2))
+        cu.preprocess(lu, ru, a)
+        cu.preprocess(lu.float(), ru.float(), b)
+        assert torch.equal(a, b)
+        a, b = (torch.zeros((2 * B, H, W, 16), dtype=dtype, device=DEV) for _ in range(2))
+        cu.stem(lu, ru, w0, b0, w1, b1, a)
+        cu.stem(lu.float(), ru.float(), w0, b0, w1, b1, b)
+        assert torch.equal(a, b)
+
+
+def test_post_confidence_score_and_points():
+    """SURVEY §8(f)2,3: batched confidence score and disparity -> points vs the oracle restatement."""
+    from oracle import post_oracle as PO
+    from s2m2_b200 import post
+    g = torch.Generator().manual_seed(5)
+    conf = torch.rand((3, 1, 352, 416), generator=g)
+    for hw, margin in (((352, 416), 100), ((301, 399), 100), ((340, 410), 7)):
+        s = post.confidence_score(conf.to(DEV), hw, margin).cpu()
+        assert torch.allclose(s, PO.confidence_score(conf, hw, margin), atol=1e-6, rtol=1e-6), (hw, margin)
+    assert torch.equal(post.confidence_score(conf.to(DEV), (301, 399)), post.confidence_score(conf.to(DEV), (301, 399)))   # deterministic
+    disp = torch.rand((2, 1, 40, 56), generator=g) * 60 - 3           # some non-positive disparities
+    occ = torch.rand((2, 1, 40, 56), generator=g)
+    cf = torch.rand((2, 1, 40, 56), generator=g)
+    kw = dict(fx=711.5, cx=27.3, cy=19.1, baseline=193.0, doffs=31.2, depth_trunc=12.0)
+    xyz, valid = post.disparity_to_points(disp.to(DEV), conf=cf.to(DEV), occ=occ.to(DEV), **kw)
+    rx, rv = PO.disparity_to_points(disp, conf=cf, occ=occ, **kw)
+    assert torch.equal(valid.cpu(), rv)
+    assert torch.allclose(xyz.cpu(), rx, rtol=1e-5, atol=1e-6)

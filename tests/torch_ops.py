@@ -143,7 +143,7 @@ class TorchOps:
     def stem(self, left, right, w0, b0, w1, b1, out):
         dev = left.device
         w0, b0, w1, b1 = (t.to(dev) for t in (w0, b0, w1, b1))       # weights arrive as host tensors
-        x = ((torch.cat([left, right], 0) / 255.0 - 0.5) * 2)
+        x = ((torch.cat([left, right], 0).float() / 255.0 - 0.5) * 2)
         h = F.gelu(F.conv2d(x, w0[:, :, None, None], b0))
         y = F.conv2d(h, w1[:, :, None, None], b1).permute(0, 2, 3, 1)            # (2B,H,W,16)
         n, H, W, _ = y.shape
