@@ -392,7 +392,8 @@ def main():
         line["roofline_forward"] = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                                     "frac": ach / pk["tensor_sustained"], "tflop_per_pair": tf,
                                     "peak_source": pk["src"] + " bf16 sustained"}
-    line["vs_baseline_note"] = "value / 11.2 FPS (reference README TensorRT fp16 on ONE RTX 5090, L@1216x1024; BASELINE.md section 1)"
+    line["vs_baseline_note"] = ("value / 11.2 FPS (reference README TensorRT fp16 on ONE RTX 5090, L@1216x1024, single-pair protocol; "
+                                "BASELINE.md section 1) - value is batched throughput, single_pair.pairs_per_s / 11.2 is the like-for-like ratio")
     if world == 1 and not args.no_cpu_baseline:
         from oracle import s2m2_oracle as O
         cores = host_threads()
