@@ -11,8 +11,9 @@ architecture, synthetic images — there is no network for checkpoints/datasets)
 (config 3, the protocol of the reference's README FPS table) is reported beside it as `single_pair`.
   value      pairs/s with the inputs already resident in HBM (CUDA-graph replay of the whole forward),
              CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-  e2e        the same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of both
-             images and D2H read of disparity/occlusion/confidence inside the timed region, every step.
+  e2e        the same metric through the public runtime call (s2m2_b200.runtime.PipelinedRunner.run) with HOST (pinned)
+             inputs: H2D copy of both images and D2H read of disparity/occlusion/confidence inside the timed region, every
+             step; the copies of neighbouring steps overlap the compute of the current one on a second stream.
   roofline   dominant kernel = the implicit-GEMM convolution; the heaviest conv shape of the model is timed
              alone with CUDA events; achieved = 2*M*N*K / time against MEASURED_PEAKS.json (burst figure).
   cpu_baseline  the oracle (port of the reference's fp32 algorithm) on the host cores, rank 0, N=1 only.
@@ -203,32 +204,17 @@ def main():
     left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
     left, right = left_h.to(dev), right_h.to(dev)
 
-    # ---- warm-up (also builds packed weights, PE tables, func attributes), then capture the forward in a CUDA graph
+    # ---- the serving runtime (s2m2_b200/runtime.py): warm-up, CUDA-graph capture of the forward, double-buffered host pipeline
+    from s2m2_b200.runtime import PipelinedRunner
+    n0 = model.ops.launch_count()
+    runner = PipelinedRunner(model, B, H, W, dev, use_graph=not args.no_graph)      # 2 eager forwards (+ 1 captured)
+    launches_per_fwd = (model.ops.launch_count() - n0) // (2 if args.no_graph else 3)
+    graph = runner.graph
+    runner.left.copy_(left)
+    runner.right.copy_(right)
+    left, right = runner.left, runner.right
     with torch.inference_mode():
-        out = model(left, right)
-        torch.cuda.synchronize()
-        n0 = model.ops.launch_count()
-        out = model(left, right)
-        torch.cuda.synchronize()
-        launches_per_fwd = model.ops.launch_count() - n0
-        graph = None
-        if not args.no_graph:
-            del out
-            torch.cuda.empty_cache()      # the eager warm-up's cached blocks would otherwise sit beside the graph's private pool
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=s):
-                    out = model(left, right)
-            torch.cuda.current_stream().wait_stream(s)
-
-        def step():
-            if graph is not None:
-                graph.replay()
-            else:
-                model(left, right)
-
+        step = runner.replay                      # device-resident inputs: one graph replay per step
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
@@ -249,31 +235,25 @@ def main():
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
 
-        # ---- e2e: public nn.Module call with host inputs / host outputs, every step
+        # ---- e2e: the runtime's public call with HOST inputs / outputs: every step copies its two pinned host images to the
+        # device and its three maps back; the copies of step i+1 / i-1 ride a second stream under the compute of step i
         host_out = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(3)]
+        comp = torch.cuda.current_stream()
 
-        def e2e_step():
-            if graph is not None:
-                left.copy_(left_h, non_blocking=True)      # H2D into the graph's static input buffers
-                right.copy_(right_h, non_blocking=True)
-                graph.replay()
-                res = out
-            else:
-                res = model(left_h.to(dev, non_blocking=True), right_h.to(dev, non_blocking=True))
-            for h, t in zip(host_out, res):
-                h.copy_(t, non_blocking=True)
-        for _ in range(2):
-            e2e_step()
+        def e2e_run(n):
+            runner.run([(left_h, right_h)] * n, host_out=[host_out] * n)
+            comp.wait_stream(runner.copy_stream)      # the last device->host copy is inside the timed region
+        e2e_run(2)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         e3.record()
         torch.cuda.synchronize()
         ms_e2e = e2.elapsed_time(e3)
+        out = runner.out
 
         # ---- the same end-to-end call fed with uint8 images (4x fewer H2D bytes, bit-identical outputs); eager launches
         e2e_u8 = None
@@ -304,33 +284,22 @@ def main():
         # ---- single-pair latency (BASELINE config 3, the protocol behind the reference's README FPS): batch 1, rank 0
         single = None
         if rank == 0 and B != 1:
-            l1, r1 = left[:1].clone(), right[:1].clone()
-            for _ in range(2):
-                model(l1, r1)
-            g1 = None
-            if not args.no_graph:
-                torch.cuda.empty_cache()
-                s1 = torch.cuda.Stream()
-                s1.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s1):
-                    g1 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1, stream=s1):
-                        model(l1, r1)
-                torch.cuda.current_stream().wait_stream(s1)
-            one = (lambda: g1.replay()) if g1 is not None else (lambda: model(l1, r1))
+            r1 = PipelinedRunner(model, 1, H, W, dev, use_graph=not args.no_graph)
+            r1.left.copy_(left[:1])
+            r1.right.copy_(right[:1])
             for _ in range(3):
-                one()
+                r1.replay()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n1 = max(args.steps, 5)
             torch.cuda.synchronize()
             a0.record()
             for _ in range(n1):
-                one()
+                r1.replay()
             a1.record()
             torch.cuda.synchronize()
             ms1 = a0.elapsed_time(a1) / n1
             single = {"batch": 1, "ms_per_pair": ms1, "pairs_per_s": 1e3 / ms1, "steps": n1}
-            del g1
+            del r1
 
         # ---- roofline of the dominant kernel (implicit-GEMM conv), heaviest shape timed alone (rank 0)
         roof = None
