@@ -101,3 +101,24 @@ def test_schedule_fp16_packing_matches_golden():
     assert d.dtype == torch.float32 and torch.isfinite(d).all()
     assert (d - g["disp"]).abs().mean() < 2e-3, float((d - g["disp"]).abs().mean())
     assert (o - g["occ"]).abs().mean() < 1e-3 and (c - g["conf"]).abs().mean() < 1e-3
+
+
+def test_space_to_depth_repack_of_conv1_down_is_exact():
+    """model._pack_d0: Conv2d(16, 64, 5, stride 2, pad 2) == 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth input with the
+    repacked weights (taps that fall outside the 5x5 window are zero)."""
+    import torch.nn.functional as F
+    m = S2M2(32, 1, 1, use_positivity=True, refine_iter=1, precision="fp16")
+    m.my_load_state_dict(random_state_dict(32, 1, 3))
+    m._ensure_packed(torch.device("cpu"))
+    d0 = m._packed["bb"]["d0"]
+    assert (d0.kh, d0.kw, d0.stride, d0.cin, d0.cout) == (3, 3, 1, 64, 64)
+    w5 = m._w("cnn_backbone.conv1_down.0.weight").half().float()          # the packed weights are the fp16-rounded originals
+    b5 = m._w("cnn_backbone.conv1_down.0.bias").float()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 16, 12, 20), generator=g)
+    ref = F.conv2d(x, w5, b5, stride=2, padding=2)
+    n, c, H, W = x.shape
+    xs = x.permute(0, 2, 3, 1).reshape(n, H // 2, 2, W // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, H // 2, W // 2, 4 * c)
+    w3 = d0.w.float().reshape(64, 3, 3, 64).permute(0, 3, 1, 2)
+    got = F.conv2d(xs.permute(0, 3, 1, 2), w3, d0.b, stride=1, padding=1)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
