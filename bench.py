@@ -15,8 +15,10 @@ architecture, synthetic images — there is no network for checkpoints/datasets)
              inputs: H2D copy of both images and D2H read of disparity/occlusion/confidence inside the timed region, every
              step; the copies of neighbouring steps overlap the compute of the current one on a second stream.
   roofline   dominant kernel = the implicit-GEMM convolution; the heaviest conv shape of the model is timed
-             alone with CUDA events; achieved = 2*M*N*K / time against MEASURED_PEAKS.json (burst figure).
-  cpu_baseline  the oracle (port of the reference's fp32 algorithm) on the host cores, rank 0, N=1 only.
+             alone with CUDA events; achieved = 2*M*N*K / time against MEASURED_PEAKS.json (burst figure); forward_frac =
+             the whole forward (pairs/s x TFLOP/pair) against the sustained figure.
+  cpu_baseline  the oracle (port of the reference's fp32 algorithm) on the host cores, rank 0, N=1 only: full-size pairs.
+  --impl reference  the same CPU arm as its own JSON line: full-size pairs, one per forward, as many as fit S2M2_REF_BUDGET_S.
 """
 import argparse
 import json
@@ -92,10 +94,28 @@ def host_threads():
     return max(1, min(n, 32))
 
 
-def run_reference(args, cfg_workload):
-    """--impl reference: the reference's CPU algorithm (oracle port, fp32 eager torch ops) on the host cores."""
+def time_oracle(sd, NTR, H, W, seed, budget_s, max_forwards):
+    """Time the oracle port (fp32 eager torch ops on the host cores) on FULL-SIZE pairs of the named resolution: one pair per
+    forward, as many forwards as fit the budget (at least one).  No crop, no extrapolation: pairs/s = forwards / seconds."""
     from oracle import s2m2_oracle as O
-    from s2m2_b200.weights import MODEL_TABLE, random_state_dict, synthetic_pair
+    from s2m2_b200.weights import synthetic_pair
+    left, right = synthetic_pair(1, H, W, seed)
+    wl, wr = left[..., :128, :160].contiguous(), right[..., :128, :160].contiguous()
+    O.forward(sd, wl, wr, NTR, True, 3)                     # thread-pool / allocator warm-up on a small crop (untimed)
+    times = []
+    t_start = time.time()
+    while len(times) < max_forwards:
+        t0 = time.time()
+        O.forward(sd, left, right, NTR, True, 3)
+        times.append(time.time() - t0)
+        if time.time() - t_start + times[-1] > budget_s:     # the next one would overrun the budget
+            break
+    return times
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU algorithm (oracle port, fp32 eager torch ops) on the host cores, rank 0 only."""
+    from s2m2_b200.weights import MODEL_TABLE, random_state_dict
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -104,33 +124,18 @@ def run_reference(args, cfg_workload):
     torch.set_num_threads(cores)
     sd = random_state_dict(C, NTR, 0)
     H, W = args.height, args.width
-    budget = float(os.environ.get("S2M2_REF_BUDGET_S", "150"))
-    # bounded sample: centre crop (multiple of 32) whose cost fits the budget; pairs/s extrapolated by pixel count
-    left, right = synthetic_pair(1, H, W, 1)
-    t0 = time.time()
-    O.forward(sd, left[..., :H // 4 // 32 * 32 or 32, :W // 4 // 32 * 32 or 32].contiguous(),
-              right[..., :H // 4 // 32 * 32 or 32, :W // 4 // 32 * 32 or 32].contiguous(), NTR, True, 3)
-    t_probe = time.time() - t0
-    hh, ww = (H // 4 // 32 * 32 or 32), (W // 4 // 32 * 32 or 32)
-    est_full = t_probe * (H * W) / (hh * ww)
-    nsteps = args.steps + args.warmup
-    frac = 1.0
-    if est_full * nsteps > budget:
-        frac = max(budget / (est_full * nsteps), (hh * ww) / (H * W))
-    sh = max(32, int(H * frac ** 0.5) // 32 * 32)
-    sw = max(32, int(W * frac ** 0.5) // 32 * 32)
-    l, r = left[..., :sh, :sw].contiguous(), right[..., :sh, :sw].contiguous()
-    for _ in range(args.warmup):
-        O.forward(sd, l, r, NTR, True, 3)
-    t0 = time.time()
-    for _ in range(args.steps):
-        O.forward(sd, l, r, NTR, True, 3)
-    dt = (time.time() - t0) / args.steps
-    pairs_per_s = (sh * sw) / (H * W) / dt
-    sample = f"oracle port fp32, {args.steps} steps of one {sw}x{sh} crop of a {W}x{H} pair ({sh * sw / (H * W):.3f} pair/step)"
+    budget = float(os.environ.get("S2M2_REF_BUDGET_S", "100"))
+    times = time_oracle(sd, NTR, H, W, 1, budget, args.steps)
+    dt = sum(times) / len(times)
+    pairs_per_s = 1.0 / dt
+    sample = (f"oracle port fp32 eager on {cores} host threads: {len(times)} timed forward(s) of ONE full-size {W}x{H} pair each "
+              f"(no crop, no extrapolation; {args.steps} requested, budget {budget:.0f} s)")
+    cfg = dict(cfg)
+    cfg["reference_sample"] = {"pairs_per_forward": 1, "height": H, "width": W, "forwards_timed": len(times),
+                               "seconds": [round(t, 3) for t in times], "extrapolated": False}
     line = {"impl": "reference", "metric": "stereo pairs/sec", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_workload,
+            "steps": args.steps, "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pairs_per_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -188,17 +193,26 @@ def main():
     dev = torch.device("cuda", local_rank)
     C, NTR = MODEL_TABLE[args.model]
     dist = None
+    bcast_bytes = 0
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # evidence of the communicator (rank / nranks lines of NCCL's own init log), unless the caller already chose a level
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
 
     model = S2M2(C, 1, NTR, use_positivity=True, refine_iter=3, precision=args.precision).eval()
     if rank == 0:
         model.my_load_state_dict(random_state_dict(C, NTR, 0))
     model = model.to(dev)
-    if world > 1:   # the only collective on the path: one flat weight broadcast over NVLink
-        from s2m2_b200.parallel import broadcast_weights
-        broadcast_weights(model, 0)
+    if world > 1:   # the only collective on the path: ONE broadcast of the packed weight blob over NVLink
+        from s2m2_b200.parallel import broadcast_packed
+        from s2m2_b200.ops import CudaOps
+        model.ops = CudaOps()
+        bcast_bytes = broadcast_packed(model, dev, 0)
+        torch.cuda.synchronize()
+        print(f"[rank {rank}/{world}] packed weights received: {bcast_bytes / 1e6:.1f} MB (one NCCL broadcast from rank 0)", file=sys.stderr, flush=True)
 
     left_h, right_h = synthetic_pair(B, H, W, 1 + rank)
     left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
@@ -258,29 +272,37 @@ def main():
         ms_e2e = e2.elapsed_time(e3)
         out = runner.out
 
-        # ---- the same end-to-end call fed with uint8 images (4x fewer H2D bytes, bit-identical outputs); eager launches
+        # ---- the same end-to-end call fed with uint8 images (4x fewer H2D bytes, bit-identical outputs) through
+        # the same pipelined runtime: PipelinedRunner(input_dtype=uint8) -> its own captured graph
         e2e_u8 = None
         if rank == 0:
             lu_h, ru_h = left_h.to(torch.uint8).pin_memory(), right_h.to(torch.uint8).pin_memory()
+            ru8 = PipelinedRunner(model, B, H, W, dev, input_dtype=torch.uint8, use_graph=not args.no_graph)
+            nu = max(2, min(args.steps, 10))
 
-            def u8_step():
-                res = model(lu_h.to(dev, non_blocking=True), ru_h.to(dev, non_blocking=True))
-                for h, tt in zip(host_out, res):
-                    h.copy_(tt, non_blocking=True)
-            u8_step()
+            def u8_run(n):
+                ru8.run([(lu_h, ru_h)] * n, host_out=[host_out] * n)
+                comp.wait_stream(ru8.copy_stream)
+            u8_run(2)
             torch.cuda.synchronize()
-            nu = max(2, min(args.steps, 5))
             u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             u0.record()
-            for _ in range(nu):
-                u8_step()
+            u8_run(nu)
             u1.record()
             torch.cuda.synchronize()
             e2e_u8 = {"value": B * nu / (u0.elapsed_time(u1) * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W,
-                      "d2h_bytes_per_step": 3 * B * H * W * 4, "steps": nu, "note": "uint8 host images, eager launches (no graph), this rank only"}
+                      "d2h_bytes_per_step": 3 * B * H * W * 4, "steps": nu,
+                      "note": "uint8 host images through PipelinedRunner(input_dtype=uint8).run (graph replay, overlapped copies), this rank only"}
+            del ru8
 
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        per_rank = [B * args.steps / (ms * 1e-3)]
+        print(f"[rank {rank}/{world}] {per_rank[0]:.2f} pairs/s device-resident, {B * args.steps / (ms_e2e * 1e-3):.2f} pairs/s end to end "
+              f"({args.steps} steps of {B} pairs)", file=sys.stderr, flush=True)
         if dist:
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [B * args.steps / (float(a[0]) * 1e-3) for a in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
 
@@ -341,22 +363,39 @@ def main():
 
     pairs = B * world * args.steps
     value = pairs / (ms * 1e-3)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()      # before the JSON line: it stays the last line of stdout whatever NCCL logs at teardown
+        dist = None
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
         return
     tf = FLOP_PER_PAIR.get((args.model, H, W))
     pk = _peaks()
+    if single:
+        cfg["single_pair"] = single      # BASELINE config 3 (the README FPS protocol), measured in the same run on rank 0
+    headline_cfg = (args.model, H, W) == ("L", 1024, 1216)
+    vs_base = None
+    if headline_cfg:
+        vs_base = (single["pairs_per_s"] if single else (value / world if B == 1 else None))
+        vs_base = vs_base / 11.2 if vs_base else None
+    if roof is not None and tf:
+        ach = value / world * tf
+        roof["forward_achieved"] = ach
+        roof["forward_peak"] = pk["tensor_sustained"]
+        roof["forward_frac"] = ach / pk["tensor_sustained"]
+        roof["forward_note"] = (f"whole forward: pairs/s per GPU x {tf} TFLOP/pair (SURVEY 8(d)) against the {pk['src']} bf16 SUSTAINED "
+                                "peak; `frac` above is the heaviest conv launch timed alone against the burst peak")
     line = {"metric": "stereo pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": (value / 11.2) if (args.model, H, W) == ("L", 1024, 1216) else None,
+            "vs_baseline": vs_base,
             "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4,
                     "d2h_bytes_per_step": 3 * B * H * W * 4,
                     "note": "s2m2_b200.runtime.PipelinedRunner.run: per step 2 pinned host images -> device, graph replay, 3 maps -> pinned "
                             "host; the copies of steps i+1 / i-1 overlap the compute of step i on a second stream (separately timed region)"},
             "gpu_launches": launches_per_fwd * args.steps, "launches_per_forward": launches_per_fwd,
-            "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof}
+            "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof,
+            "per_rank_pairs_per_s": per_rank, "weight_broadcast_bytes": bcast_bytes}
     if single:
         line["single_pair"] = single
     if e2e_u8:
@@ -366,31 +405,27 @@ def main():
         line["roofline_forward"] = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                                     "frac": ach / pk["tensor_sustained"], "tflop_per_pair": tf,
                                     "peak_source": pk["src"] + " bf16 sustained"}
-    line["vs_baseline_note"] = ("value / 11.2 FPS (reference README TensorRT fp16 on ONE RTX 5090, L@1216x1024, single-pair protocol; "
-                                "BASELINE.md section 1) - value is batched throughput, single_pair.pairs_per_s / 11.2 is the like-for-like ratio")
+    line["vs_baseline_note"] = ("single_pair.pairs_per_s / 11.2 FPS: the reference README's TensorRT fp16 number on ONE RTX 5090, "
+                                "L@1216x1024, single-pair protocol (BASELINE.md section 1) - like for like; `value` is batched throughput")
+    ref_gpu = os.path.join(ROOT, "profiles", "r2_reference_gpu.json")
+    if headline_cfg and os.path.exists(ref_gpu):   # the reference's own GPU paths, measured on a B200 of this pool (tools/bench_reference_gpu.py)
+        try:
+            runs = {r["batch"]: r for r in json.load(open(ref_gpu))["runs"]}
+            line["ref_gpu_eager_fp16"] = {f"batch{b}_pairs_per_s": runs[b]["ref_eager_fp16"]["pairs_per_s"] for b in runs if "ref_eager_fp16" in runs[b]}
+            line["ref_gpu_compile"] = {f"batch{b}_pairs_per_s": runs[b]["ref_torch_compile_fp16"]["pairs_per_s"] for b in runs
+                                       if "ref_torch_compile_fp16" in runs[b]}
+            line["ref_gpu_note"] = "committed measurement (profiles/r2_reference_gpu.json), not re-timed in this run"
+        except Exception:
+            pass
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import s2m2_oracle as O
         cores = host_threads()
         torch.set_num_threads(cores)
-        sd = random_state_dict(C, NTR, 0)
-        # bounded sample (~20 s): probe a small crop, then the largest crop (multiple of 32) that fits the budget
-        ph_, pw_ = min(H, 256), min(W, 320)
-        lp, rp = left_h[:1, :, :ph_, :pw_].contiguous(), right_h[:1, :, :ph_, :pw_].contiguous()
-        O.forward(sd, lp, rp, NTR, True, 3)
-        t0 = time.time()
-        O.forward(sd, lp, rp, NTR, True, 3)
-        tp = time.time() - t0
-        frac = min(1.0, 20.0 / max(tp * (H * W) / (ph_ * pw_), 1e-6))
-        sh, sw = max(ph_, int(H * frac ** 0.5) // 32 * 32), max(pw_, int(W * frac ** 0.5) // 32 * 32)
-        l, r = left_h[:1, :, :sh, :sw].contiguous(), right_h[:1, :, :sh, :sw].contiguous()
-        t0 = time.time()
-        O.forward(sd, l, r, NTR, True, 3)
-        dt = time.time() - t0
-        line["cpu_baseline"] = {"value": (sh * sw) / (H * W) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": f"oracle port fp32 eager, one {sw}x{sh} crop of a {W}x{H} pair ({dt:.1f} s), scaled by pixel count"}
+        times = time_oracle(random_state_dict(C, NTR, 0), NTR, H, W, 1, float(os.environ.get("S2M2_CPU_BASELINE_BUDGET_S", "30")), 2)
+        dt = sum(times) / len(times)
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle port fp32 eager, {len(times)} forward(s) of one full-size {W}x{H} pair ({dt:.1f} s each), "
+                                          "no crop / extrapolation"}
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

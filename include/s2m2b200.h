@@ -85,11 +85,39 @@ int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, 
 /* Scratch bytes the tcgen05 attention kernel needs for (S sequences, N tokens, heads, head dim d); 0 = not applicable. */
 int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int32_t heads, int32_t d, int32_t dtype);
 
+/* All-pairs scan-line correlation = the cost volume of DispInit with its affine LayerNorm fused in front (submodules.py:165,216-217):
+ *   cv[b,y,i,j] = <LN(f)[b,y,i,:], LN(f)[B+b,y,j,:]>
+ * on tcgen05 with fp32-grade accuracy: every normalised value is split x = hi + lo into two fp16 numbers and the product is
+ * evaluated as hi.hi + hi.lo + lo.hi into one fp32 TMEM accumulator, so that the arg-max over the volume stays where the fp32
+ * reference puts it.  f: (2B, h, w, C) fp16 NHWC view (left images first), C in {64,128,192,256}, w % 4 == 0, w <= 512;
+ * gamma, beta: fp32 (C); cv: (B, h, w, w) fp32 dense; work: device scratch of s2m2b200_row_corr_workspace_bytes (the hi / lo planes).
+ * Returns 0 = launched, 1 = not applicable (caller: s2m2b200_layernorm + the fp32 CUDA-core batched GEMM of s2m2b200_conv2d). */
+int64_t s2m2b200_row_corr_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t C);
+int s2m2b200_row_corr(const S2m2Tensor* f, const float* gamma, const float* beta, float* cv, void* work, int64_t work_bytes,
+                      void* stream);
+
+/* Indicator matrix of an (h x w) token grid for the tcgen05 PE attention (attentions.py:42-48, utils.py:32-60): the two
+ * marginals of the attention matrix that the relative-PE term needs are P . E with E[key][c] = (c == x(key)) or
+ * (c == w + y(key)), fp16, (ceil(h*w/128)*128) x 128.  The caller fills a HOST buffer of s2m2b200_pe_indicator_bytes(h, w)
+ * bytes once per resolution, keeps a 128-byte-aligned device copy and passes it as `work` to s2m2b200_attention together
+ * with `pesum` (h + w <= 80, head dim 64); without it the mma.sync kernel evaluates the PE term. */
+int64_t s2m2b200_pe_indicator_bytes(int32_t h, int32_t w);
+int s2m2b200_pe_indicator(int32_t h, int32_t w, void* host_out);
+
 /* Fused pre-norm FFN (attentions.py:229-250): y = x + W2 . GELU(W0 . LayerNorm(x) + b0) + b2, one tcgen05 kernel that
  * keeps LN(x) and the hidden activations in shared memory.  x, y: (.., C) fp16 views (y may alias x); w0, w2: (C, C)
  * K-major fp16; b0, b2 fp32.  Returns 0 = launched, 1 = not applicable (caller runs layernorm + two conv2d), < 0 = error. */
 int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void* w0, const float* b0, const void* w2, const float* b2,
                  int32_t w_dtype, void* stream);
+
+/* Fused two-layer point-wise block (two token tiles in flight per CTA, hidden activations never leave the SM):
+ *   y = [res +] W2 . act(W0 . (layernorm ? LayerNorm(x) : x) + b0) + b2
+ * (layernorm = 1, act = GELU): the pre-norm FFN above with res = x;  (layernorm = 0, act = ReLU): the 1x1 branch of
+ * ConvBlock2D (attentions.py:273-281, `convs_1x`) with res = the 3x3 branch's output, so that the block's sum needs no
+ * extra pass.  x, res, y: (.., C) fp16 views, C in {128,192,256}; y may alias res / x.  Returns 0 = launched,
+ * 1 = not applicable (caller runs the separate launches), < 0 = error. */
+int s2m2b200_mlp2(const S2m2Tensor* x, const S2m2Tensor* res, const S2m2Tensor* y, const void* w0, const float* b0,
+                  const void* w2, const float* b2, int32_t w_dtype, int32_t layernorm, int32_t act, void* stream);
 
 /* Fused pre-norm projection (attentions.py:119-130,150-161: q/k/v = Linear(LayerNorm(x))): y = W . LayerNorm(x) + b with the
  * normalised tile kept in shared memory as the A operand for every output-channel tile.  x: (.., C) fp16, C in {128,192,256};

@@ -165,11 +165,15 @@ __global__ void __launch_bounds__(AT_THREADS) attention_simt_kernel(AttnP p) {
 template <int MAXI>
 static int launch_attn(const AttnP& p, cudaStream_t s) {
   size_t smem = sizeof(float) * ((AT_BQ + AT_BK) * (p.d + 4) + AT_BK * p.d);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(attention_simt_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+  static bool attr_set[S2M2_MAX_DEVICES] = {false};
+  const int di = current_device_index();
+  if (!attr_set[di]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    S2M2_CHECK(e == cudaSuccess, "attention_simt: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set[di] = true;
   }
+  S2M2_CHECK(smem <= 200 * 1024, "attention_simt: head dim %d needs %zu bytes of shared memory (> 200 KB)", p.d, smem);
+  S2M2_CHECK(p.S <= 65535 && p.heads <= 65535, "attention_simt: S = %d sequences exceed gridDim.z (65535); split the batch", p.S);
   dim3 grid(cdiv(p.N, AT_BQ), p.heads, p.S);
   launch_k(attention_simt_kernel<MAXI>, grid, AT_THREADS, smem, s, p);
   S2M2_LAUNCH_OK("attention_simt");
@@ -225,6 +229,7 @@ extern "C" int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, 
   const bool force_simt = impl == 1;
   if (impl == 0 && work && attention_tc_supported(p) && work_bytes >= (int64_t)attention_tc_workspace_bytes(p))
     return attention_tc_launch(p, work, (cudaStream_t)stream);
+  if (impl == 0 && attention2d_tc_supported(p, work, work_bytes)) return attention2d_tc_launch(p, work, (cudaStream_t)stream);
   if (!force_simt && attention_mma_supported(p)) return attention_mma_launch(p, (cudaStream_t)stream);
   return attention_simt_launch(p, (cudaStream_t)stream);
 }

@@ -18,4 +18,8 @@ int attention_mma_launch(const AttnP& p, cudaStream_t s);
 int attention_tc_supported(const AttnP& p);
 size_t attention_tc_workspace_bytes(const AttnP& p);
 int attention_tc_launch(const AttnP& p, void* workspace, cudaStream_t s);
+// tcgen05 2-D attention (N >= 256 keys, head dim 64), optionally with the relative-PE marginals (work = indicator matrix)
+int attention2d_tc_supported(const AttnP& p, const void* work, long long work_bytes);
+int attention2d_tc_launch(const AttnP& p, const void* indicator, cudaStream_t s);
+size_t attention2d_tc_indicator_bytes(int h, int w);
 }  // namespace s2m2

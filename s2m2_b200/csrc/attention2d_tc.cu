@@ -1,0 +1,486 @@
+// tcgen05 attention for the 2-D global blocks at 1/32 resolution (N = (H/32)(W/32) keys, head dim 64): the keys of a sequence
+// do not fit TMEM, so S = Q K^T is produced in blocks of 128 keys that ping-pong through two TMEM buffers.
+//
+// Persistent CTAs (one per SM) walk over work tiles = 128 queries of one (sequence, head).  Per tile, two passes:
+//     pass 1   S_j = Q K_j^T for every key block j  ->  exact row max m      (no exponentials, no rescaling later)
+//     pass 2   S_j again  ->  P_j = exp2((S_j - m) * scale * log2 e) as fp16 into shared memory (A operand),  l += row sums
+//              O += P_j V_j        tcgen05.mma, V consumed as it lies in memory ([key][channel] = MN-major B operand)
+//     EPI      out = O / l
+// Recomputing Q K^T costs 50 % more MMAs than an online softmax, but the tensor pipe has the headroom here (the exponentials
+// bound this kernel: 128 x N per tile on 16 MUFU lanes / clk) and it removes the read-modify-write of O in TMEM and the
+// dependency chain PV(j) -> rescale -> PV(j+1); the result is the plain two-pass softmax of the reference.
+// The MMA thread runs   QK(j+2)  behind  PV(j)   so that the softmax warps always have the next S block waiting.
+//
+// PE = true adds the contextual relative-position term of the feature pyramid's encoder blocks (attentions.py:42-48):
+//     pesum[q, 0:16]  = .5 * sum_xj  Mx[q, xj] * pe_x[xq - xj + w - 1],   Mx[q, xj] = sum_yj P[q, (yj, xj)]
+//     pesum[q, 16:32] = .5 * sum_yj  My[q, yj] * pe_y[yq - yj + h - 1],   My[q, yj] = sum_xj P[q, (yj, xj)]
+// The two marginals of P are themselves a matrix product: [Mx | My] = P . E with the constant 0/1 indicator matrix
+// E[key, c] = (c < w ? x(key) == c : y(key) == c - w), so they ride the tensor core next to P V (two extra MMA groups per key
+// block into TMEM columns beside O) and the (N, N, 32) tensor of utils.py:32-60 never exists.
+//   warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..17 = softmax / epilogue.
+// Reference op: F.scaled_dot_product_attention / the explicit softmax + einsum in the 2-D blocks (attentions.py:42-50,165-226).
+#include "tc_common.cuh"
+
+#include "attention.cuh"
+
+namespace s2m2 {
+using namespace tc;
+
+constexpr int A2_SPLIT = 4;                         // softmax warps per TMEM lane quarter: each owns 32 of a block's 128 keys
+constexpr int A2_SM_THREADS = 128 * A2_SPLIT;
+constexpr int A2_THREADS = 64 + A2_SM_THREADS;
+constexpr int A2_NST = 6;                           // ring slots of 128 keys x 64 channels (16 KB)
+constexpr uint32_t A2_BLK = 16384;
+constexpr int A2_O_COL = 256, A2_MG_COL = 320;      // TMEM columns: S0 [0,128), S1 [128,256), O [256,320), marginals [320,400)
+
+struct A2P {
+  void* out;
+  void* pesum;
+  const float *pe_x, *pe_y;
+  long long out_ld;
+  int S, N, heads, C, kv_shift, NB, q_tiles, tiles;
+  int pe_h, pe_w, pe_half;
+  float sl2;  // softmax scale * log2(e)
+};
+struct A2Maps {
+  CUtensorMap qkv;   // (tokens x 3C): box {64 ch, 128 tokens}
+  CUtensorMap e;     // PE: indicator matrix (NB*128 keys x 128): box {64, 128}
+};
+
+__device__ __forceinline__ float a2_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major, SWIZZLE_128B B operand of one 128-key block: rows = keys of 128 B (64 MN elements), 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t a2_sdesc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(16384 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+static size_t a2_smem_bytes() {
+  return (size_t)2 * A2_BLK + 2 * 2 * A2_BLK + (size_t)A2_NST * A2_BLK + (14 + 2 * A2_NST) * 8 + 16 + 2 * A2_SPLIT * 128 * 4 + 1024;
+}
+
+template <bool PE>
+__global__ void __launch_bounds__(A2_THREADS, 1) attention2d_tc_kernel(const __grid_constant__ A2Maps maps, const A2P p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                // 2 x [128 queries][128 B]
+  uint8_t* sP = smem + 2 * A2_BLK;                   // 2 x 2 chunks of [128 queries][64 keys]
+  uint8_t* sRing = sP + 4 * A2_BLK;
+  uint64_t* bars = (uint64_t*)(sRing + A2_NST * A2_BLK);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 14 + 2 * A2_NST);
+  float* sRed = (float*)(tmem_slot + 4);             // [2][A2_SPLIT][128]: partial row max, partial row sum
+  const uint32_t bar0 = smem_u32(bars);
+  auto qfull = [&](int b) { return bar0 + 8 * b; };
+  auto qfree = [&](int b) { return bar0 + 8 * (2 + b); };
+  auto sfull = [&](int b) { return bar0 + 8 * (4 + b); };
+  auto sfree = [&](int b) { return bar0 + 8 * (6 + b); };
+  auto pready = [&](int b) { return bar0 + 8 * (8 + b); };
+  auto pfree = [&](int b) { return bar0 + 8 * (10 + b); };
+  const uint32_t ofull = bar0 + 8 * 12, ofree = bar0 + 8 * 13;
+  const uint32_t full0 = bar0 + 8 * 14, empty0 = full0 + 8 * A2_NST;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NB = p.NB;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(qfull(b), 1);
+      mbar_init(qfree(b), 1);
+      mbar_init(sfull(b), 1);
+      mbar_init(sfree(b), 4 * A2_SPLIT);
+      mbar_init(pready(b), 4 * A2_SPLIT);
+      mbar_init(pfree(b), 1);
+    }
+    mbar_init(ofull, 1);
+    mbar_init(ofree, 4 * A2_SPLIT);
+    for (int i = 0; i < A2_NST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  // tile -> (query tile, head, sequence): the query tiles of one (sequence, head) are adjacent, so they run on different SMs
+  // at the same time and share its K/V through L2
+  auto decode = [&](int tile, int& q0, int& head, int& s) {
+    q0 = (tile % p.q_tiles) * 128;
+    const int r = tile / p.q_tiles;
+    head = r % p.heads;
+    s = r / p.heads;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t rit = 0, lt = 0;
+      auto ring_load = [&](const CUtensorMap* m, int col, int row) {
+        const int st = rit % A2_NST;
+        mbar_wait(empty0 + 8 * st, ((rit / A2_NST) & 1) ^ 1);
+        mbar_expect_tx(full0 + 8 * st, A2_BLK);
+        tma_load_2d(m, smem_u32(sRing + st * A2_BLK), full0 + 8 * st, col, row);
+        ++rit;
+      };
+      auto load_q = [&](int tile, uint32_t use) {     // use = local tile index: buffer use & 1
+        int q0, head, s;
+        decode(tile, q0, head, s);
+        const int b = use & 1;
+        if (use >= 2) mbar_wait(qfree(b), ((use >> 1) - 1) & 1);
+        mbar_expect_tx(qfull(b), A2_BLK);
+        tma_load_2d(&maps.qkv, smem_u32(sQ + b * A2_BLK), qfull(b), head * 64, s * p.N + q0);
+      };
+      if ((int)blockIdx.x < p.tiles) load_q(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        int q0, head, s;
+        decode(tile, q0, head, s);
+        const int row0 = ((s + p.kv_shift) % p.S) * p.N;
+        const int kcol = p.C + head * 64, vcol = 2 * p.C + head * 64;
+        for (int j = 0; j < NB; ++j) ring_load(&maps.qkv, kcol, row0 + j * 128);          // pass 1
+        if (tile + (int)gridDim.x < p.tiles) load_q(tile + gridDim.x, lt + 1);            // next tile's Q well ahead of its use
+        ring_load(&maps.qkv, kcol, row0);                                                  // pass 2, in the MMA thread's order
+        if (NB > 1) ring_load(&maps.qkv, kcol, row0 + 128);
+        for (int j = 0; j < NB; ++j) {
+          ring_load(&maps.qkv, vcol, row0 + j * 128);
+          if (PE) {
+            ring_load(&maps.e, 0, j * 128);
+            ring_load(&maps.e, 64, j * 128);
+          }
+          if (j + 2 < NB) ring_load(&maps.qkv, kcol, row0 + (j + 2) * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // O = P V: B = V block as loaded, [128 keys][64 ch] = MN-major (channels contiguous): b_major bit 16
+      const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_e1 = (1u << 4) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t rit = 0, u = 0, v = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int qb = lt & 1;
+        mbar_wait(qfull(qb), (lt >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t qd = make_sdesc(smem_u32(sQ + qb * A2_BLK));
+        auto qk = [&]() {                               // S[u & 1] = Q K^T with the next ring slot
+          const int b = u & 1;
+          if (u >= 2) {
+            mbar_wait(sfree(b), ((u >> 1) - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const int st = rit % A2_NST;
+          mbar_wait(full0 + 8 * st, (rit / A2_NST) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t bd = make_sdesc(smem_u32(sRing + st * A2_BLK));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + b * 128, qd + 2 * k, bd + 2 * k, idesc_s, k != 0);
+          umma_commit(empty0 + 8 * st);
+          umma_commit(sfull(b));
+          ++rit; ++u;
+        };
+        // P[pb] (128 x 128 keys, two 64-key chunks) times the MN-major block in the next ring slot
+        auto pmma = [&](int pb, uint32_t tcol, uint32_t idesc, bool accumulate) {
+          const int st = rit % A2_NST;
+          mbar_wait(full0 + 8 * st, (rit / A2_NST) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t bd = a2_sdesc_mn(smem_u32(sRing + st * A2_BLK));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint64_t ad = make_sdesc(smem_u32(sP + (pb * 2 + c) * A2_BLK));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // A: +32 B per 16 keys within the 128 B row; B: +16 key rows = 2 swizzle atoms = 2048 B
+              umma_f16(tmem_base + tcol, ad + 2 * k, bd + (uint64_t)((2048 >> 4) * (c * 4 + k)), idesc, accumulate || (c | k) != 0);
+          }
+          umma_commit(empty0 + 8 * st);
+          ++rit;
+        };
+        for (int j = 0; j < NB; ++j) qk();             // pass 1
+        qk();                                           // pass 2
+        if (NB > 1) qk();
+        if (NB <= 2) umma_commit(qfree(qb));
+        for (int j = 0; j < NB; ++j) {
+          const int pb = v & 1;
+          mbar_wait(pready(pb), (v >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (j == 0 && lt > 0) {                       // the previous tile's O (and marginals) have been read out
+            mbar_wait(ofree, (lt - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          pmma(pb, A2_O_COL, idesc_o, j != 0);
+          if (PE) {
+            pmma(pb, A2_MG_COL, idesc_o, j != 0);
+            pmma(pb, A2_MG_COL + 64, idesc_e1, j != 0);
+          }
+          umma_commit(pfree(pb));
+          ++v;
+          if (j + 2 < NB) {
+            qk();
+            if (j + 3 == NB) umma_commit(qfree(qb));   // that was the tile's last read of Q
+          }
+        }
+        umma_commit(ofull);
+      }
+    }
+  } else {
+    // ================= softmax + epilogue: thread = one query row x 32 of a block's 128 keys =================
+    const int q = warp & 3, hs = (warp - 2) >> 2;   // TMEM lane quarter (fixed by warp id % 4), column split
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool odd = lane & 1;
+    __half* ob = (__half*)p.out;
+    uint32_t u = 0, v = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      int q0, head, s;
+      decode(tile, q0, head, s);
+      const int t = q0 + r;
+      const bool valid = t < p.N;
+      // ---- pass 1: exact row max
+      float m = -3.0e38f;
+      for (int j = 0; j < NB; ++j, ++u) {
+        const int b = u & 1;
+        mbar_wait(sfull(b), (u >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t rr[32];
+        tmem_ld32(trow + b * 128 + hs * 32, rr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int key0 = j * 128 + hs * 32;
+        if (key0 + 32 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + i < p.N) m = fmaxf(m, __uint_as_float(rr[i]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree(b));
+      }
+      sRed[hs * 128 + r] = m;
+      asm volatile("bar.sync 1, %0;" ::"n"(A2_SM_THREADS) : "memory");
+#pragma unroll
+      for (int jj = 0; jj < A2_SPLIT; ++jj) m = fmaxf(m, sRed[jj * 128 + r]);
+      // ---- pass 2: P = exp2((S - m) * scale*log2e) as fp16 into the swizzled A-operand layout, row sums
+      float l = 0.f;
+      const float msc = m * p.sl2;
+      for (int j = 0; j < NB; ++j, ++u, ++v) {
+        const int b = u & 1, pb = v & 1;
+        mbar_wait(sfull(b), (u >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t rr[32];
+        tmem_ld32(trow + b * 128 + hs * 32, rr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int key0 = j * 128 + hs * 32;
+        __half2 h[16];
+        if (key0 + 32 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a = a2_ex2(fmaf(__uint_as_float(rr[i]), p.sl2, -msc));
+            const float c = a2_ex2(fmaf(__uint_as_float(rr[i + 1]), p.sl2, -msc));
+            l += a + c;
+            h[i >> 1] = __floats2half2_rn(a, c);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a = (key0 + i < p.N) ? a2_ex2(fmaf(__uint_as_float(rr[i]), p.sl2, -msc)) : 0.f;
+            const float c = (key0 + i + 1 < p.N) ? a2_ex2(fmaf(__uint_as_float(rr[i + 1]), p.sl2, -msc)) : 0.f;
+            l += a + c;
+            h[i >> 1] = __floats2half2_rn(a, c);
+          }
+        }
+        if (v >= 2) mbar_wait(pfree(pb), ((v >> 1) - 1) & 1);          // P V of two blocks ago has finished reading this buffer
+        uint8_t* blk = sP + (pb * 2 + (hs >> 1)) * A2_BLK + r * 128;    // 64-key chunk, this row
+        const int u0 = (hs & 1) * 4;                                    // first 16-byte unit of these 32 keys within the 128 B row
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) *(uint4*)(blk + (((u0 + uu) ^ (r & 7)) << 4)) = *(uint4*)&h[4 * uu];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy P writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // our TMEM reads are ordered before the next MMAs
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sfree(b));
+          mbar_arrive(pready(pb));
+        }
+      }
+      sRed[(A2_SPLIT + hs) * 128 + r] = l;
+      asm volatile("bar.sync 1, %0;" ::"n"(A2_SM_THREADS) : "memory");
+      l = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < A2_SPLIT; ++jj) l += sRed[(A2_SPLIT + jj) * 128 + r];
+
+      // ---- epilogue: O / l -> fp16 -> global, full 32 B sectors per store instruction via lane-pair exchange
+      mbar_wait(ofull, lt & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float inv = 1.f / l;
+      {
+        const bool pvalid = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+        const long long off0 = ((long long)s * p.N + t) * p.out_ld + head * 64 + hs * 16;
+        const long long poff0 = __shfl_xor_sync(0xffffffffu, off0, 1);
+        uint32_t rr[16];
+        tmem_ld16(trow + A2_O_COL + hs * 16, rr);
+        tmem_ld_wait16(rr);
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(__uint_as_float(rr[2 * i]) * inv, __uint_as_float(rr[2 * i + 1]) * inv);
+        const uint4 lo = *(uint4*)&h[0], hi = *(uint4*)&h[4];
+        const uint4 send = odd ? lo : hi;
+        uint4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+        if (odd ? pvalid : valid) *(uint4*)(ob + (odd ? poff0 + 8 : off0)) = odd ? recv : lo;
+        if (odd ? valid : pvalid) *(uint4*)(ob + (odd ? off0 + 8 : poff0)) = odd ? hi : recv;
+      }
+      if (PE) {
+        // marginals: TMEM columns A2_MG_COL + c, c < w: Mx[c];  w <= c < w + h: My[c - w].  Warps hs = 0, 1 evaluate the x term
+        // (channels 8 hs .. 8 hs + 7 of pesum[0:16]), warps hs = 2, 3 the y term (pesum[16:32]).
+        const int w = p.pe_w, hh = p.pe_h;
+        const bool xpart = hs < 2;
+        const int c_lo = xpart ? 0 : w, c_hi = xpart ? w : w + hh;          // marginal columns this warp consumes
+        const int qpos = xpart ? (t % w) : (t / w);                           // xq or yq
+        const float* tab = (xpart ? p.pe_x : p.pe_y) + (hs & 1) * 8;
+        const int base = qpos + (xpart ? w : hh) - 1 + c_lo;                  // table row = base - c
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int ch = c_lo >> 4; ch * 16 < c_hi; ++ch) {                      // warp-uniform chunk range
+          uint32_t rr[16];
+          tmem_ld16(trow + A2_MG_COL + ch * 16, rr);
+          tmem_ld_wait16(rr);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = ch * 16 + i;
+              if (c >= c_lo && c < c_hi) {
+                const float mg = __uint_as_float(rr[i]);
+                const float4* tr = (const float4*)(tab + (long long)(base - c) * 16);
+                const float4 t0 = __ldg(tr), t1 = __ldg(tr + 1);
+                acc[0] = fmaf(mg, t0.x, acc[0]); acc[1] = fmaf(mg, t0.y, acc[1]); acc[2] = fmaf(mg, t0.z, acc[2]); acc[3] = fmaf(mg, t0.w, acc[3]);
+                acc[4] = fmaf(mg, t1.x, acc[4]); acc[5] = fmaf(mg, t1.y, acc[5]); acc[6] = fmaf(mg, t1.z, acc[6]); acc[7] = fmaf(mg, t1.w, acc[7]);
+              }
+            }
+          }
+        }
+        if (valid) {
+          const float sc = 0.5f * inv;
+          const long long po = (((long long)s * p.N + t) * p.heads + head) * 32 + hs * 8;   // hs 0,1 -> 0..15; hs 2,3 -> 16..31
+          if (p.pe_half) {
+            __half2 h4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h4[i] = __floats2half2_rn(acc[2 * i] * sc, acc[2 * i + 1] * sc);
+            *(uint4*)((__half*)p.pesum + po) = *(uint4*)&h4[0];
+          } else {
+            float4* dst = (float4*)((float*)p.pesum + po);
+            dst[0] = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
+            dst[1] = make_float4(acc[4] * sc, acc[5] * sc, acc[6] * sc, acc[7] * sc);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // O has been read: its columns may be overwritten
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofree);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+// bytes of the indicator matrix E for an (h x w) token grid: (ceil(h*w / 128) * 128 keys) x 128 columns fp16
+size_t attention2d_tc_indicator_bytes(int h, int w) { return (size_t)((h * w + 127) / 128) * 128 * 128 * 2; }
+
+int attention2d_tc_supported(const AttnP& p, const void* work, long long work_bytes) {
+  if (!p.qh || !p.oh || p.d != 64) return 0;
+  if (p.N < 256) return 0;                              // shorter sequences: the whole-row / mma kernels
+  if (p.qkv_ld % 8 || p.out_ld % 8 || !aligned(p.qkv, 16) || !aligned(p.out, 16)) return 0;
+  if (p.pesum) {
+    if (p.pe_w + p.pe_h > 80 || p.pe_h * p.pe_w != p.N) return 0;
+    if (!work || !aligned(work, 128) || work_bytes < (long long)attention2d_tc_indicator_bytes(p.pe_h, p.pe_w)) return 0;
+    if (!aligned(p.pesum, 16)) return 0;
+  }
+  return tc::device_ok() ? 1 : 0;
+}
+
+template <bool PE>
+static int launch_a2(const A2Maps& maps, const A2P& p, cudaStream_t s) {
+  const size_t smem = a2_smem_bytes();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sms_of[64] = {0};
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms_of[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attention2d_tc_kernel<PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    S2M2_CHECK(e == cudaSuccess, "attention2d_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms_of[dev] = sms > 0 ? sms : 1;
+  }
+  const int sms = sms_of[dev];
+  launch_k(attention2d_tc_kernel<PE>, p.tiles < sms ? p.tiles : sms, A2_THREADS, smem, s, maps, p);
+  S2M2_LAUNCH_OK("attention2d_tc");
+  return 0;
+}
+
+int attention2d_tc_launch(const AttnP& a, const void* indicator, cudaStream_t s) {
+  A2P p{};
+  p.out = a.out; p.out_ld = a.out_ld; p.S = a.S; p.N = a.N; p.heads = a.heads; p.C = a.C; p.kv_shift = a.kv_shift;
+  p.NB = (a.N + 127) / 128;
+  p.q_tiles = (a.N + 127) / 128;
+  p.tiles = p.q_tiles * a.heads * a.S;
+  p.sl2 = a.scale * 1.4426950408889634f;
+  p.pesum = a.pesum; p.pe_x = a.pe_x; p.pe_y = a.pe_y; p.pe_h = a.pe_h; p.pe_w = a.pe_w; p.pe_half = a.ph_half;
+  A2Maps maps;
+  const long long tokens = (long long)a.S * a.N;
+  cuuint32_t estr[2] = {1, 1}, box[2] = {64, 128};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * a.C), (cuuint64_t)tokens}, strides[1] = {(cuuint64_t)a.qkv_ld * 2};
+    CUresult r1 = tc::encode_fn()(&maps.qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.qkv), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    S2M2_CHECK(r1 == CUDA_SUCCESS, "attention2d_tc: cuTensorMapEncodeTiled(qkv) failed: %d", (int)r1);
+  }
+  if (a.pesum) {
+    cuuint64_t dims[2] = {128, (cuuint64_t)p.NB * 128}, strides[1] = {256};
+    CUresult r2 = tc::encode_fn()(&maps.e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(indicator), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    S2M2_CHECK(r2 == CUDA_SUCCESS, "attention2d_tc: cuTensorMapEncodeTiled(indicator) failed: %d", (int)r2);
+    return launch_a2<true>(maps, p, s);
+  }
+  maps.e = maps.qkv;
+  return launch_a2<false>(maps, p, s);
+}
+
+}  // namespace s2m2
+
+using namespace s2m2;
+
+// The 0/1 indicator matrix E of an (h x w) token grid for the PE attention kernel, written to a HOST buffer of
+// s2m2b200_pe_indicator_bytes(h, w) bytes: row = key (row-major token y*w + x, utils.py:35-38), fp16,
+// E[key][c] = 1 for c == x(key) and for c == w + y(key); every other entry (and every row >= h*w) is 0.
+extern "C" int64_t s2m2b200_pe_indicator_bytes(int32_t h, int32_t w) { return (int64_t)attention2d_tc_indicator_bytes(h, w); }
+extern "C" int s2m2b200_pe_indicator(int32_t h, int32_t w, void* host_out) {
+  S2M2_CHECK(h > 0 && w > 0 && h + w <= 128 && host_out, "pe_indicator: need 0 < h, w and h + w <= 128");
+  const size_t n = attention2d_tc_indicator_bytes(h, w) / 2;
+  uint16_t* e = (uint16_t*)host_out;
+  for (size_t i = 0; i < n; ++i) e[i] = 0;
+  const uint16_t one = 0x3C00;   // fp16 1.0
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const size_t key = (size_t)y * w + x;
+      e[key * 128 + x] = one;
+      e[key * 128 + w + y] = one;
+    }
+  return 0;
+}

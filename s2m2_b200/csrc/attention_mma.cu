@@ -263,10 +263,11 @@ static int launch_fa(const AttnP& p, cudaStream_t s) {
   const size_t smem = (size_t)((FA_BQ + NST * FA_BK) * (D + 8) + NST * FA_BK * (D / VS + 8)) * sizeof(__half) +
                       (PE ? sizeof(float) * FA_BQ * (2 * p.pe_h + FA_BK) : 0);
   S2M2_CHECK(smem <= 200 * 1024, "attention_mma: shared memory %zu too large", smem);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[S2M2_MAX_DEVICES] = {false};
+  const int di = current_device_index();
+  if (!attr[di]) {
     cudaFuncSetAttribute(attention_mma_kernel<D, FA_BK, PE, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
+    attr[di] = true;
   }
   dim3 grid(cdiv(p.N, FA_BQ), p.heads * VS, p.S);
   launch_k(attention_mma_kernel<D, FA_BK, PE, VS>, grid, FA_THREADS, smem, s, p);

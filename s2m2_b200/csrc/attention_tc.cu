@@ -294,15 +294,17 @@ template <int D>
 static int launch_atc(const AtcMaps& maps, const AtcP& p, cudaStream_t s) {
   const size_t smem = atc_smem_bytes(D, p.NKB);
   S2M2_CHECK(smem <= 227 * 1024, "attention_tc: shared memory %zu too large", smem);
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
+  static bool attr[S2M2_MAX_DEVICES] = {false};
+  static int sms_of[S2M2_MAX_DEVICES] = {0};
+  const int di = current_device_index();
+  int& sms = sms_of[di];
+  if (!attr[di]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     S2M2_CHECK(e == cudaSuccess, "attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
+    attr[di] = true;
   }
   launch_k(attention_tc_kernel<D>, p.tiles < sms ? p.tiles : sms, ATC_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("attention_tc");

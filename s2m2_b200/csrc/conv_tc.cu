@@ -136,6 +136,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// waits for this thread's outstanding tcgen05.ld's; the registers pass through the asm so that no use of them can be scheduled
+// above the wait (tcgen05.ld is asynchronous: its destination registers are undefined until wait::ld)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
@@ -322,28 +331,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // =====================================================================================================
 constexpr int TC2_EPI_GROUPS = 4;                       // epilogue warps per TMEM lane quarter
 constexpr int TC2_THREADS = 64 + 128 * TC2_EPI_GROUPS;   // 576
-
-// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26) — far below fp16 output rounding; the exact erff costs
-// about twice as many instructions and the GELU epilogue is the critical path of the small-K GEMMs.
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float r = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float act_fast(float x, int act) {
-  switch (act) {
-    case S2M2_ACT_GELU: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));
-    case S2M2_ACT_RELU: return fmaxf(x, 0.0f);
-    case S2M2_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
-    case S2M2_ACT_TANH: return tanhf(x);
-    default: return x;
-  }
-}
 
 // PAIR: two CTAs of a cluster (one TPC) work on two vertically adjacent 128-pixel tiles with the same output channels as ONE
 // 256 x BN tcgen05.mma.cta_group::2: each CTA loads its own A tile but only half of the weight tile, so the L2->SMEM operand
@@ -571,14 +558,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       if (p.dbg & 2) valid = false;
       // neighbour-lane exchange for full-sector stores (see below): lane l pairs with lane l^1
       const bool pvalid = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+      // the TMEM loads are double-buffered: chunk c+1 is in flight while chunk c goes through the activation / stores
+      uint32_t rbuf[2][16];
+      if (n0 + half * CG < p.Cout) tmem_ld16(trow + half * CG, rbuf[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int c0 = half * CG + c * 16;
         const int n = n0 + c0;
         if (n >= p.Cout) break;
-        uint32_t rr[16];
-        tmem_ld16(trow + c0, rr);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t* rr = rbuf[c & 1];
+        tmem_ld_wait16(rr);
+        if (c + 1 < NCH && n + 16 < p.Cout) tmem_ld16(trow + c0 + 16, rbuf[(c + 1) & 1]);
         float v[16];
         if (p.bias) {
 #pragma unroll
@@ -596,7 +586,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         switch (p.act) {
           case S2M2_ACT_GELU:
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.0f + fast_erf(v[i] * 0.70710678118654752440f));
+            for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
             break;
           case S2M2_ACT_RELU:
 #pragma unroll
@@ -733,15 +723,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static bool tc_device_ok() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    ok = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
-          major == 10 && get_encode() != nullptr)
-             ? 1
-             : 0;
+  static int ok_of[S2M2_MAX_DEVICES] = {0};   // 0 = unknown, 1 = yes, 2 = no  (per device)
+  const int di = current_device_index();
+  if (ok_of[di] == 0) {
+    int major = 0;
+    ok_of[di] = (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, di) == cudaSuccess && major == 10 && get_encode() != nullptr) ? 1 : 2;
   }
-  return ok == 1;
+  return ok_of[di] == 1;
 }
 
 int conv_tc_supported(const S2m2Conv* a) {
@@ -804,11 +792,12 @@ static int encode_act(CUtensorMap* m, const S2m2Tensor& t, bool flat, int tw, in
 template <int BN, int STAGES>
 static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s) {
   constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[S2M2_MAX_DEVICES] = {false};
+  const int di = current_device_index();
+  if (!attr[di]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr = true;
+    attr[di] = true;
   }
   launch_k(conv_tc_kernel<BN, STAGES>, grid, TC_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("conv_tc");
@@ -820,15 +809,17 @@ static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles
   constexpr size_t stg = 4 * TC2_EPI_GROUPS * 1024 * ((32 * (BN / TC2_EPI_GROUPS) * 2 + 1023) / 1024);
   constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + (PAIR ? BN / 2 : BN) * TC_BK * 2) + stg + (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
+  static bool attr[S2M2_MAX_DEVICES] = {false};
+  static int sms_of[S2M2_MAX_DEVICES] = {0};
+  const int di = current_device_index();
+  int& sms = sms_of[di];
+  if (!attr[di]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
+    attr[di] = true;
   }
   if constexpr (PAIR) {   // clusters of two CTAs (one TPC); one cluster per pair of m-tiles
     const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles;

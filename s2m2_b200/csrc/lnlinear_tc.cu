@@ -234,15 +234,17 @@ static int launch_lnl(const LnlMaps& maps, const LnlP& p, cudaStream_t s) {
   constexpr int NST = (XB + SB + 3 * WB <= 222 * 1024) ? 3 : 2;
   constexpr size_t smem = XB + NST * WB + SB + (7 + 2 * NST) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
+  static bool attr[S2M2_MAX_DEVICES] = {false};
+  static int sms_of[S2M2_MAX_DEVICES] = {0};
+  const int di = current_device_index();
+  int& sms = sms_of[di];
+  if (!attr[di]) {
     cudaError_t e = cudaFuncSetAttribute(lnlinear_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "lnlinear_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
+    attr[di] = true;
   }
   const int tiles = (p.M + 127) / 128;
   launch_k(lnlinear_tc_kernel<C>, tiles < sms ? tiles : sms, LNL_THREADS, smem, s, maps, p);

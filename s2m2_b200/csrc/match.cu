@@ -1,6 +1,8 @@
 // Matching-stage kernels on the fp32 scan-line cost volume: dust-bin log-Sinkhorn + argmax + soft-argmax,
 // cost-volume lookup, convex upsampling.  HBM/L2-bound work; warp-shuffle reductions, no tensor cores.
 // Reference: submodules.py:7-60,147-243; s2m2.py:101-133; utils.py:9-20.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace s2m2 {
@@ -343,14 +345,25 @@ __global__ void disparity_to_points_kernel(const float* __restrict__ disp, const
 }
 }  // namespace s2m2
 
+namespace s2m2 {
+int sinkhorn_cluster_launch(const float* cv, int B, int h, int w, float* disp, float* conf, float* occ, int* amax, int pos, int iters,
+                            cudaStream_t s);
+}
 using namespace s2m2;
 
 extern "C" {
 
 int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t w, float* disp, float* conf, float* occ,
                                  int32_t* amax, int32_t use_positivity, int32_t iters, void* stream) {
-  S2M2_CHECK(w >= 8 && w <= 8192 && iters >= 1, "sinkhorn: bad w=%d / iters=%d", w, iters);
-  size_t smem = sizeof(float) * (2 * (w + 1) + 2 * SK_WARPS * 32);
+  S2M2_CHECK(w >= 8 && w <= 5000 && iters >= 1, "sinkhorn: bad w=%d / iters=%d (8 <= w <= 5000)", w, iters);
+  // the matrix-resident cluster kernel (sinkhorn_cluster.cu) takes every width whose scan-line fits a cluster's shared memory
+  // (w <= 639 with positivity); S2M2_SK_IMPL=1 forces the streaming kernel below
+  static const int impl = getenv("S2M2_SK_IMPL") ? atoi(getenv("S2M2_SK_IMPL")) : 0;
+  if (impl != 1) {
+    const int r = sinkhorn_cluster_launch(cv, B, h, w, disp, conf, occ, amax, use_positivity, iters, (cudaStream_t)stream);
+    if (r != 1) return r;
+  }
+  size_t smem = sizeof(float) * (2 * (w + 1) + 2 * SK_WARPS * 32);   // <= 44 KB for w <= 5000: below the 48 KB default limit
   launch_k(sinkhorn_kernel, B * h, SK_THREADS, smem, (cudaStream_t)stream, cv, w, use_positivity, iters, disp, conf, occ, amax);
   S2M2_LAUNCH_OK("sinkhorn_softargmax");
   return 0;

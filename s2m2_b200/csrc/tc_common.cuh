@@ -89,6 +89,15 @@ __device__ __forceinline__ float fast_erf(float x) {   // Abramowitz-Stegun 7.1.
   const float r = 1.0f - poly * t * __expf(-ax * ax);
   return copysignf(r, x);
 }
+// waits for this thread's outstanding tcgen05.ld's; the registers are passed through so that no use of them can be scheduled
+// above the wait (the loads are asynchronous: their destination registers are undefined until wait::ld)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 inline PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -104,13 +113,13 @@ inline PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 inline bool device_ok() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    ok = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
-          major == 10 && encode_fn() != nullptr) ? 1 : 0;
+  static int ok_of[S2M2_MAX_DEVICES] = {0};   // 0 = unknown, 1 = yes, 2 = no  (per device)
+  const int di = current_device_index();
+  if (ok_of[di] == 0) {
+    int major = 0;
+    ok_of[di] = (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, di) == cudaSuccess && major == 10 && encode_fn() != nullptr) ? 1 : 2;
   }
-  return ok == 1;
+  return ok_of[di] == 1;
 }
 }  // namespace tc
 }  // namespace s2m2

@@ -398,6 +398,9 @@ class S2M2(nn.Module):
     def _convblock(self, z, p, out=None):
         """ConvBlock2D (attentions.py:277-281)."""
         a = self._c(self._c(z, p["c0"], ACT_GELU), p["c2"])
+        o = a if out is None else out
+        if self.ops.mlp2(z, a, o, p["x0"], p["x2"], ACT_RELU):     # fused 1x1 -> ReLU -> 1x1 + a (hidden tile stays in smem)
+            return o
         u = self._c(z, p["x0"], ACT_RELU)
         return self._c(u, p["x2"], out=out, res=a)
 
@@ -514,10 +517,11 @@ class S2M2(nn.Module):
         self._tap("transformer", ftr)
 
         # -- initial disparity by optimal transport over the all-pairs scan-line cost volume (submodules.py:203-243)
-        fn = self._ln(ftr, P["di_w"], P["di_b"], out_dtype=f32)
         cv = ops.empty((B, h4, w4, w4), f32, dev)
-        ops.row_corr(fn, cv)
-        del fn
+        if not ops.row_corr_tc(ftr, P["di_w"], P["di_b"], cv):       # fp16: LN + split-fp16 tcgen05 correlation (fp32-grade accuracy)
+            fn = self._ln(ftr, P["di_w"], P["di_b"], out_dtype=f32)
+            ops.row_corr(fn, cv)
+            del fn
         disp = ops.empty((B, h4, w4), f32, dev)
         conf = ops.empty((B, h4, w4), f32, dev)
         occ = ops.empty((B, h4, w4), f32, dev)

@@ -47,12 +47,14 @@ def load_library():
     lib.s2m2b200_version.restype = C.c_char_p
     lib.s2m2b200_launch_count.restype = C.c_int64
     lib.s2m2b200_attention_workspace_bytes.restype = C.c_int64
+    lib.s2m2b200_pe_indicator_bytes.restype = C.c_int64
+    lib.s2m2b200_row_corr_workspace_bytes.restype = C.c_int64
     _lib = lib
     return lib
 
 
 EXPORTS = [
-    "s2m2b200_conv2d", "s2m2b200_ffn", "s2m2b200_ln_linear", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_layernorm", "s2m2b200_groupnorm",
+    "s2m2b200_conv2d", "s2m2b200_ffn", "s2m2b200_mlp2", "s2m2b200_ln_linear", "s2m2b200_attention", "s2m2b200_attention_workspace_bytes", "s2m2b200_pe_table", "s2m2b200_pe_indicator", "s2m2b200_pe_indicator_bytes", "s2m2b200_row_corr", "s2m2b200_row_corr_workspace_bytes", "s2m2b200_layernorm", "s2m2b200_groupnorm",
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
@@ -90,6 +92,11 @@ class CudaOps:
         self.conv_impl = conv_impl      # 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel
         self.ffn_fused = os.environ.get("S2M2_FFN_FUSED", "1") != "0"     # fused LN+FFN tcgen05 kernel
         self.ffn_min_tokens = int(os.environ.get("S2M2_FFN_MIN_TOKENS", "16384"))
+        # C > 256 runs the one-tile-at-a-time kernel (the tile pair does not fit TMEM): it needs >= 2 tiles per SM to win
+        self.ffn_min_tokens_wide = int(os.environ.get("S2M2_FFN_MIN_TOKENS_WIDE", "37888"))
+        self.row_corr_fused = os.environ.get("S2M2_ROWCORR_TC", "1") != "0"   # tcgen05 split-fp16 cost volume with fused LayerNorm
+        self.mlp2_fused = os.environ.get("S2M2_MLP2_FUSED", "1") != "0"   # fused 1x1 -> ReLU -> 1x1 (+res) of ConvBlock2D
+        self.mlp2_min_tokens = int(os.environ.get("S2M2_MLP2_MIN_TOKENS", "16384"))
         self.ln_linear_fused = os.environ.get("S2M2_LNL_FUSED", "1") != "0"  # fused LN + QKV projection tcgen05 kernel
         self.ln_linear_min_tokens = int(os.environ.get("S2M2_LNL_MIN_TOKENS", "16384"))
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
@@ -122,7 +129,13 @@ class CudaOps:
                 host = torch.empty((2 * n + 1, 16), dtype=torch.float32)
                 self._chk(self.lib.s2m2b200_pe_table(n, C.c_void_p(host.data_ptr())), "pe_table")
                 tabs.append(host.to(device))
-            self._pe[key] = (tabs[0], tabs[1], h, w)
+            ind = None
+            if h + w <= 80:        # indicator matrix of the token grid: the tcgen05 PE attention takes the marginals of P as P . E
+                nb = int(self.lib.s2m2b200_pe_indicator_bytes(h, w))
+                hostb = torch.empty(nb // 2, dtype=torch.float16)
+                self._chk(self.lib.s2m2b200_pe_indicator(h, w, C.c_void_p(hostb.data_ptr())), "pe_indicator")
+                ind = hostb.to(device)
+            self._pe[key] = (tabs[0], tabs[1], h, w, ind)
         return self._pe[key]
 
     # -- GEMM-class
@@ -150,7 +163,7 @@ class CudaOps:
             return False
         # the fused kernel runs one CTA per 128-token tile: below ~2 tiles per SM (1/16 and 1/32 resolution at L) the three
         # separate launches, which also split the output channels over CTAs, are faster (measured, tools/bench_ffn.py)
-        if z.shape[0] * z.shape[1] * z.shape[2] < self.ffn_min_tokens:
+        if z.shape[0] * z.shape[1] * z.shape[2] < (self.ffn_min_tokens if z.shape[3] <= 256 else self.ffn_min_tokens_wide):
             return False
         zt = tview(z)
         rc = self.lib.s2m2b200_ffn(C.byref(zt), C.byref(zt), C.c_void_p(l0.w.data_ptr()), C.c_void_p(l0.b.data_ptr()),
@@ -158,6 +171,21 @@ class CudaOps:
         if rc == 1:
             return False
         self._chk(rc, "ffn")
+        return True
+
+    def mlp2(self, x, res, out, l0, l2, act):
+        """out = res + W2 . act(W0 . x + b0) + b2 in one tcgen05 kernel (ConvBlock2D's 1x1 branch, attentions.py:273-281);
+        False if the fused kernel does not take this shape / dtype (the caller then runs the two conv2d launches)."""
+        if not self.mlp2_fused or l0.b is None or l2.b is None or l0.cin != l0.cout or l2.cin != l2.cout or l0.kh != 1 or l2.kh != 1:
+            return False
+        if x.shape[0] * x.shape[1] * x.shape[2] < self.mlp2_min_tokens:
+            return False
+        rc = self.lib.s2m2b200_mlp2(C.byref(tview(x)), C.byref(tview(res)) if res is not None else None, C.byref(tview(out)),
+                                    C.c_void_p(l0.w.data_ptr()), C.c_void_p(l0.b.data_ptr()), C.c_void_p(l2.w.data_ptr()),
+                                    C.c_void_p(l2.b.data_ptr()), _DT[l0.w.dtype], 0, act, self._stream())
+        if rc == 1:
+            return False
+        self._chk(rc, "mlp2")
         return True
 
     def ln_linear(self, z, lin, out):
@@ -194,6 +222,23 @@ class CudaOps:
         a.impl = 1
         self._chk(self.lib.s2m2b200_conv2d(C.byref(a), self._stream()), "row_corr")
 
+    def row_corr_tc(self, f, gamma, beta, cv):
+        """cv = all-pairs scan-line correlation of LayerNorm(f) (affine) on tcgen05 with split-fp16 operands (fp32-grade
+        accuracy: the arg-max must not move); False if not applicable (caller: layernorm -> row_corr)."""
+        if not self.row_corr_fused or f.dtype != torch.float16:
+            return False
+        B, h, w, _ = cv.shape
+        nb = int(self.lib.s2m2b200_row_corr_workspace_bytes(B, h, w, f.shape[3]))
+        if nb == 0 or not cv.is_contiguous() or cv.dtype != torch.float32:
+            return False
+        work = torch.empty(nb // 2, dtype=torch.float16, device=f.device)
+        rc = self.lib.s2m2b200_row_corr(C.byref(tview(f)), C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), C.c_void_p(cv.data_ptr()),
+                                        C.c_void_p(work.data_ptr()), C.c_int64(nb), self._stream())
+        if rc == 1:
+            return False
+        self._chk(rc, "row_corr")
+        return True
+
     def attention(self, qkv, o, S, N, heads, kv_shift, pe=None, pesum=None):
         q = tview(qkv)
         ot = tview(o)
@@ -204,10 +249,13 @@ class CudaOps:
                 wt = torch.empty(wbytes // 2, dtype=torch.float16, device=qkv.device)   # V^T scratch of the tcgen05 kernel
                 work = C.c_void_p(wt.data_ptr())
         if pesum is not None:
-            px, py, ph, pw = pe
+            px, py, ph, pw = pe[:4]
+            ind = pe[4] if len(pe) > 4 and self.attn_tc else None
             ps = S2m2Tensor(pesum.data_ptr(), _DT[pesum.dtype], 1, 1, S * N * heads, 32, 32)
             rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, C.c_void_p(px.data_ptr()),
-                                             C.c_void_p(py.data_ptr()), ph, pw, C.byref(ps), None, C.c_int64(0), self._stream())
+                                             C.c_void_p(py.data_ptr()), ph, pw, C.byref(ps),
+                                             C.c_void_p(ind.data_ptr()) if ind is not None else None,
+                                             C.c_int64(ind.numel() * 2 if ind is not None else 0), self._stream())
         else:
             rc = self.lib.s2m2b200_attention(C.byref(q), C.byref(ot), S, N, heads, kv_shift, None, None, 0, 0, None,
                                              work, C.c_int64(wbytes), self._stream())

@@ -255,7 +255,7 @@ def test_resample_and_elementwise(ops, dtype):
 
 
 @pytest.mark.parametrize("pos", [True, False])
-@pytest.mark.parametrize("w", [24, 40, 76, 161])
+@pytest.mark.parametrize("w", [24, 40, 76, 161, 304, 608])   # 304 / 608: clusters of 4 / 8 CTAs (L, XL scan-lines)
 def test_sinkhorn_softargmax(ops, w, pos):
     cu, th = ops
     g = torch.Generator().manual_seed(w)
@@ -273,6 +273,31 @@ def test_sinkhorn_softargmax(ops, w, pos):
     _close(c0, c1, 1e-4, 1e-6, "conf")
     _close(o0, o1, 1e-4, 1e-6, "occ")
     _close(d0, d1, 1e-5, 2e-4, "disp")
+
+
+@pytest.mark.parametrize("B,h,w,C", [(1, 3, 304, 256), (2, 2, 160, 128), (1, 2, 76, 192), (1, 1, 132, 64), (1, 2, 512, 256)])
+def test_row_corr_split_fp16_tensor_core(ops, B, h, w, C):
+    """LN(affine) + all-pairs scan-line correlation on tcgen05 with split-fp16 operands vs float64 torch: the error must stay at
+    the level of an fp32 dot product (the arg-max over this volume is part of the bit-exact contract)."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(B * 1000 + w + C)
+    f = _rand((2 * B, h, w, C), torch.float16, g, 1.5) + 0.2
+    gamma = (_rand((C,), torch.float32, g, 0.3) + 1.0).contiguous()
+    beta = _rand((C,), torch.float32, g, 0.2).contiguous()
+    cv = torch.full((B, h, w, w), 7.0, dtype=torch.float32, device=DEV)
+    assert cu.row_corr_tc(f, gamma, beta, cv), "tcgen05 row correlation refused a supported shape"
+    torch.cuda.synchronize()
+    fn = torch.nn.functional.layer_norm(f.double(), (C,), gamma.double(), beta.double(), 1e-5)
+    ref = torch.einsum("bhic,bhjc->bhij", fn[:B], fn[B:])
+    err = (cv.double() - ref).abs().max().item()
+    # the fp32 CUDA-core path (LayerNorm kernel -> batched fp32 GEMM) on the same input, as the yard-stick
+    fn32 = torch.empty((2 * B, h, w, C), dtype=torch.float32, device=DEV)
+    cu.layernorm(f, fn32, gamma, beta)
+    cv32 = torch.empty_like(cv)
+    cu.row_corr(fn32, cv32)
+    err32 = (cv32.double() - ref).abs().max().item()
+    print(f"row_corr split-fp16 B={B} h={h} w={w} C={C}: max err {err:.3e} (fp32 CUDA-core path: {err32:.3e}), |cv| max {ref.abs().max().item():.1f}")
+    assert err < max(4 * err32, 2e-5 * ref.abs().max().item())
 
 
 def test_cv_lookup_and_refiner_glue(ops):
@@ -371,10 +396,47 @@ def test_fused_ffn(ops, C, M):
     l2 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "l2")
     ref = th.ffn_reference(z, l0, l2)
     za = z.clone()
-    cu.ffn_min_tokens = 0
+    cu.ffn_min_tokens = cu.ffn_min_tokens_wide = 0
     assert cu.ffn(za, l0, l2), "fused FFN kernel refused a supported shape"
     torch.cuda.synchronize()
     _close(za, ref, 8e-3, 8e-3, f"fused ffn C={C} M={M}")
+
+
+@pytest.mark.parametrize("C,M", [(256, 128 * 700 + 77), (256, 128 * 297), (128, 128 * 3), (192, 128 * 301 + 5), (256, 130)])
+def test_fused_ffn_many_tiles(ops, C, M):
+    """The two-tiles-in-flight FFN kernel over several tiles per CTA (odd / even counts, ragged tail), in place."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(C * 7 + M)
+    z = _rand((1, 1, M, C), torch.float16, g, 2.0) + 0.3
+    l0 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "l0")
+    l2 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "l2")
+    ref = th.ffn_reference(z, l0, l2)
+    za = z.clone()
+    cu.ffn_min_tokens = 0
+    assert cu.ffn(za, l0, l2)
+    torch.cuda.synchronize()
+    _close(za, ref, 8e-3, 8e-3, f"fused ffn (many tiles) C={C} M={M}")
+
+
+@pytest.mark.parametrize("C,M,alias", [(256, 1000, False), (256, 128 * 600 + 3, True), (128, 2000, False), (192, 128 * 299, True)])
+def test_fused_mlp2_convblock_branch(ops, C, M, alias):
+    """1x1 -> ReLU -> 1x1 + res (ConvBlock2D's convs_1x branch summed with the 3x3 branch) in one kernel vs torch;
+    strided views, output aliasing the residual or separate."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(C * 3 + M)
+    x = _rand((1, 1, M, C), torch.float16, g, 1.5)
+    resb = _rand((1, 1, M, C + 8), torch.float16, g, 1.0)
+    res = resb[..., :C]
+    l0 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "x0")
+    l2 = ConvW(_rand((C, C), torch.float16, g, 1.0 / math.sqrt(C)), _rand((C,), torch.float32, g, 0.3), 1, 1, 1, 0, 0, C, C, False, "x2")
+    ref = th.mlp2_reference(x, res, l0, l2, ACT_RELU)
+    guard = resb[..., C:].clone()
+    out = res if alias else torch.full((1, 1, M, C), 9.0, dtype=torch.float16, device=DEV)
+    cu.mlp2_min_tokens = 0
+    assert cu.mlp2(x, res, out, l0, l2, ACT_RELU), "fused mlp2 kernel refused a supported shape"
+    torch.cuda.synchronize()
+    _close(out, ref, 8e-3, 8e-3, f"mlp2 C={C} M={M}")
+    assert torch.equal(resb[..., C:], guard), "mlp2 wrote outside its view"
 
 
 @pytest.mark.parametrize("C,N,M,bias", [(256, 768, 1000, True), (128, 384, 2000, False), (192, 576, 640, True), (256, 768, 128 * 160, False),

@@ -3,8 +3,10 @@
   (b) the oracle restatement run on the same seeded inputs (on the GPU in fp32 with TF32 disabled for the
       larger sizes so that it finishes in seconds),
   (c) size-independent properties at the BASELINE sizes.
-Tolerances: fp32 mode — EPE < 1e-3 px (north_star), arg-max index identical; fp16 mode — the reference's own
-autocast-fp16 yard-stick (EPE 7e-3, l_inf 0.63 px) with head-room, stated per test.
+Tolerances (north_star): EPE < 1e-3 px against the fp32 reference in BOTH precisions, and the integer contract — arg-max index
+(submodules.py:226), conf > .2 (refinenet.py:65) and the per-iteration x - disp >= 0 mask (s2m2.py:179) — bit-identical in both
+precisions at the BASELINE sizes, on the softened test inputs AND on the un-softened BASELINE.md §4 inputs.  The tiny golden models
+(C = 32/64) in fp16 are additionally judged against the reference algorithm's own autocast-fp16 behaviour.
 """
 import pytest
 import torch
@@ -33,6 +35,16 @@ def _oracle_gpu(sd, left, right, NTR, pos, it, taps=None):
         return O.forward(sdg, left.to(DEV), right.to(DEV), NTR, pos, it, taps)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _decision_mismatches(taps, ot, n_it):
+    """Mismatch counts of the three discrete decisions of the path: prob_max_ind (submodules.py:226), conf > .2
+    (refinenet.py:65) and the occlusion mask x - disp >= 0 of every refine iteration (s2m2.py:179; the refiner's sigmoid
+    output is never exactly 0, so the zero pattern of occ after the iteration IS the mask)."""
+    flips = int((taps["disp_init.argmax"].cpu() != ot["disp_init.argmax"].cpu()).sum())
+    conf = int(((taps["disp_init.conf"].cpu() > 0.2) != (ot["disp_init.conf"].cpu() > 0.2)).sum())
+    occ = [int(((taps[f"refiner.{it}.occ"].cpu() == 0) != (ot[f"refiner.{it}.occ"].cpu() == 0)).sum()) for it in range(n_it)]
+    return flips, conf, occ
 
 
 def _margin_report(taps_mine, ot):
@@ -122,49 +134,55 @@ def test_fp16_path_no_worse_than_reference_autocast(name):
     assert (c - g["conf"]).abs().mean() < max(2 * (ac[2].float().cpu() - g["conf"]).abs().mean().item(), 5e-3)
 
 
-def test_s_640x480_vs_oracle_on_gpu():
-    """BASELINE config 2 (S, 640x480): fp32 CUDA path vs the oracle (fp32, TF32 off) on identical inputs."""
+@pytest.mark.parametrize("smooth", [True, False])
+def test_s_640x480_vs_oracle_on_gpu(smooth):
+    """BASELINE config 2 (S, 640x480): both precisions vs the oracle (fp32, TF32 off) on identical inputs — EPE < 1e-3 px and the
+    integer contract bit-identical; `smooth=False` is the raw-noise input of BASELINE.md section 4."""
     C, NTR = 128, 1
     sd = random_state_dict(C, NTR, 0)
-    left, right = synthetic_pair(1, 480, 640, 1)
-    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3)]
-    m = _model(C, NTR, sd)
-    out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
-    epe = (out[0] - ref[0]).abs().mean().item()
-    print(f"S 640x480 fp32: EPE {epe:.3e} max {(out[0] - ref[0]).abs().max().item():.3e}")
-    assert epe < 1e-3
-    assert (out[1] - ref[1]).abs().mean() < 1e-3 and (out[2] - ref[2]).abs().mean() < 1e-3
-    m16 = _model(C, NTR, sd, precision="fp16")
-    out16 = [t.cpu() for t in m16(left.to(DEV), right.to(DEV))]
-    epe16 = (out16[0] - ref[0]).abs().mean().item()
-    print(f"S 640x480 fp16: EPE {epe16:.3e} max {(out16[0] - ref[0]).abs().max().item():.3e}")
-    assert epe16 < 5e-2
-
-
-def test_l_1216x1024_headline_config_vs_oracle_on_gpu():
-    """BASELINE config 3 (L, 1216x1024, refine_iter=3), the headline: both precisions vs the fp32 oracle (TF32 off)."""
-    C, NTR = 256, 3
-    sd = random_state_dict(C, NTR, 0)
-    left, right = synthetic_pair(1, 1024, 1216, 1)
+    left, right = synthetic_pair(1, 480, 640, 1, smooth=smooth)
     ot = {}
     ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3, ot)]
-    am_ref = ot["disp_init.argmax"].cpu()
-    del ot
-    torch.cuda.empty_cache()
-    for prec, tol in (("fp32", 1e-3), ("fp16", 1e-3)):
+    for prec, tol in (("fp32", 1e-4), ("fp16", 1e-3)):
         m = _model(C, NTR, sd, precision=prec)
         m.taps = {}
         out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
-        flips = int((m.taps["disp_init.argmax"].cpu() != am_ref).sum())
+        flips, conf_mm, occ_mm = _decision_mismatches(m.taps, ot, 3)
+        epe = (out[0] - ref[0]).abs().mean().item()
+        print(f"S 640x480 {prec} smooth={smooth}: EPE {epe:.3e} max {(out[0] - ref[0]).abs().max().item():.3e} "
+              f"argmax flips {flips} conf>.2 mismatches {conf_mm} occ-mask mismatches {occ_mm}")
+        assert epe < tol
+        assert (out[1] - ref[1]).abs().mean() < tol and (out[2] - ref[2]).abs().mean() < tol
+        assert flips == 0 and conf_mm == 0 and occ_mm == [0, 0, 0]
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_l_1216x1024_headline_config_vs_oracle_on_gpu(smooth):
+    """BASELINE config 3 (L, 1216x1024, refine_iter=3), the headline: both precisions vs the fp32 oracle (TF32 off): EPE < 1e-3 px,
+    arg-max index / conf > .2 / per-iteration occlusion masks bit-identical — asserted for fp16 (the benchmarked mode) as well."""
+    C, NTR = 256, 3
+    sd = random_state_dict(C, NTR, 0)
+    left, right = synthetic_pair(1, 1024, 1216, 1, smooth=smooth)
+    ot = {}
+    ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3, ot)]
+    keep = ["disp_init.argmax", "disp_init.conf"] + [f"refiner.{it}.occ" for it in range(3)]
+    ot = {k: ot[k].cpu() for k in keep}
+    torch.cuda.empty_cache()
+    for prec, tol in (("fp32", 1e-4), ("fp16", 1e-3)):
+        m = _model(C, NTR, sd, precision=prec)
+        m.taps = {}
+        out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+        flips, conf_mm, occ_mm = _decision_mismatches(m.taps, ot, 3)
         m.taps = None
         err = (out[0] - ref[0]).abs()
-        print(f"L 1216x1024 {prec}: EPE {err.mean().item():.3e} max {err.max().item():.3e} argmax flips {flips}/{am_ref.numel()} "
+        print(f"L 1216x1024 {prec} smooth={smooth}: EPE {err.mean().item():.3e} max {err.max().item():.3e} argmax flips {flips}/"
+              f"{ot['disp_init.argmax'].numel()} conf>.2 mismatches {conf_mm} occ-mask mismatches {occ_mm} "
               f"occ {(out[1] - ref[1]).abs().mean().item():.2e} conf {(out[2] - ref[2]).abs().mean().item():.2e}")
         assert torch.isfinite(out[0]).all()
         assert err.mean().item() < tol           # north_star: EPE < 1e-3 px vs the fp32 reference
-        if prec == "fp32":
-            assert flips == 0
-        if prec == "fp16":
+        assert (out[1] - ref[1]).abs().mean() < tol and (out[2] - ref[2]).abs().mean() < tol
+        assert flips == 0 and conf_mm == 0 and occ_mm == [0, 0, 0]   # north_star: bit-exact arg-max index and occlusion masks
+        if prec == "fp16" and smooth:
             # BASELINE config 5's per-GPU share is a batch of pairs: pair 0 of a batch (with a different second pair) must
             # reproduce the single-pair result at the headline size (pairs are independent units, SURVEY §8e)
             l2, r2 = synthetic_pair(1, 1024, 1216, 7)
@@ -175,6 +193,41 @@ def test_l_1216x1024_headline_config_vs_oracle_on_gpu():
                   f"max {db.max().item():.3e}")
             assert eb.mean().item() < tol and db.mean().item() < 1e-4
             assert not torch.equal(ob[0][1], ob[0][0])               # the second pair is a different problem
+        del m
+        torch.cuda.empty_cache()
+
+
+def test_l_1216x1024_fp16_vs_real_reference_golden():
+    """The headline config against the REAL reference (tests/golden/l_c256_1216x1024_raw.npz, made by oracle/make_golden_l.py
+    from the unmodified module on CPU, un-softened inputs): outputs at every 4th pixel, their full-resolution means, and the
+    integer contract (arg-max index, conf > .2, per-iteration occlusion masks) bit-identical in fp16 and fp32."""
+    import numpy as np
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "l_c256_1216x1024_raw.npz"))
+    C, NTR, B, H, W, _, IT, wseed, iseed = [int(v) for v in z["cfg"]]
+    sd = random_state_dict(C, NTR, wseed)
+    left, right = synthetic_pair(B, H, W, iseed, smooth=False)
+    h4, w4 = H // 4, W // 4
+    unpack = lambda a: torch.from_numpy(np.unpackbits(a)[:B * h4 * w4].reshape(B, 1, h4, w4).astype(bool))
+    for prec, tol in (("fp32", 1e-4), ("fp16", 1e-3)):
+        m = _model(C, NTR, sd, precision=prec)
+        m.taps = {}
+        out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
+        taps, m.taps = m.taps, None
+        for name, t, mean in zip(("disp", "occ", "conf"), out, z["mean"]):
+            err = (t[..., ::4, ::4] - torch.from_numpy(z[name + "_s4"])).abs()
+            print(f"L golden {prec} {name}: mean err {err.mean().item():.3e} max {err.max().item():.3e} | full-res mean {t.double().mean().item():.6f} vs {mean:.6f}")
+            assert err.mean().item() < tol
+            assert abs(t.double().mean().item() - float(mean)) < tol
+        flips = int((taps["disp_init.argmax"].cpu().reshape(B, h4, w4) != torch.from_numpy(z["argmax"].astype(np.int64)).reshape(B, h4, w4)).sum())
+        conf_mm = int(((taps["disp_init.conf"].cpu().reshape(B, 1, h4, w4) > 0.2) != unpack(z["conf_mask"])).sum())
+        occ_mm = [int(((taps[f"refiner.{i}.occ"].cpu().reshape(B, 1, h4, w4) != 0) != unpack(z[f"occ_mask{i}"])).sum()) for i in range(IT)]
+        print(f"L golden {prec}: argmax flips {flips} conf>.2 mismatches {conf_mm} occ-mask mismatches {occ_mm}")
+        assert (taps["disp_init.disp"].cpu().reshape(B, 1, h4, w4) - torch.from_numpy(z["di_disp"])).abs().max() < 2e-3
+        for i in range(IT):
+            assert (taps[f"refiner.{i}.disp"].cpu().reshape(B, 1, h4, w4) - torch.from_numpy(z[f"it{i}_disp"])).abs().mean() < tol
+        assert flips == 0 and conf_mm == 0 and occ_mm == [0] * IT
         del m
         torch.cuda.empty_cache()
 
@@ -190,7 +243,9 @@ def test_other_model_sizes_vs_oracle(model_type, H, W):
     ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3, ot)]
     am_ref = ot["disp_init.argmax"].cpu()
     del ot
-    for prec, tol in (("fp32", 1e-3), ("fp16", 5e-3)):
+    # fp16 on these SMALL images (a 96 / 80-token 1/32 grid, outputs of a few px): measured 2.2e-3 px (M) with 0 arg-max flips —
+    # fp16 rounding through the refiners, not a discrete flip; the north-star 1e-3 bound is asserted at the BASELINE sizes above
+    for prec, tol in (("fp32", 1e-4), ("fp16", 4e-3)):
         m = _model(C, NTR, sd, precision=prec)
         m.taps = {}
         out = [t.cpu() for t in m(left.to(DEV), right.to(DEV))]
@@ -198,8 +253,7 @@ def test_other_model_sizes_vs_oracle(model_type, H, W):
         err = (out[0] - ref[0]).abs()
         print(f"{model_type} {W}x{H} {prec}: EPE {err.mean().item():.3e} max {err.max().item():.3e} argmax flips {flips}/{am_ref.numel()}")
         assert err.mean().item() < tol
-        if prec == "fp32":
-            assert flips == 0
+        assert flips == 0
         del m
         torch.cuda.empty_cache()
 
@@ -218,7 +272,8 @@ def test_xl_2432x2048_config_runs_and_matches_oracle():
     ref = [t.cpu() for t in _oracle_gpu(sd, left, right, NTR, True, 3)]
     err = (out[0] - ref[0]).abs()
     print(f"XL 2432x2048 fp16: EPE {err.mean().item():.3e} max {err.max().item():.3e} occ {(out[1] - ref[1]).abs().mean().item():.2e}")
-    assert err.mean().item() < 5e-3
+    assert err.mean().item() < 1e-3          # measured 4.4e-5 (round 1)
+    assert (out[1] - ref[1]).abs().mean() < 1e-3 and (out[2] - ref[2]).abs().mean() < 1e-3
 
 
 def test_output_upsample_branch_matches_reference_golden():
@@ -226,7 +281,7 @@ def test_output_upsample_branch_matches_reference_golden():
     cfg, g = load_golden(GOLDEN_UP2)
     sd = random_state_dict(cfg["C"], cfg["NTR"], cfg["wseed"], cfg["gain"])
     left, right = synthetic_pair(cfg["B"], cfg["H"], cfg["W"], cfg["iseed"])
-    for prec, tol in (("fp32", 2e-4), ("fp16", 2e-2)):
+    for prec, tol in (("fp32", 2e-5), ("fp16", 1e-3)):       # measured 3.5e-6 / 3.3e-4
         m = S2M2(cfg["C"], 1, cfg["NTR"], use_positivity=cfg["pos"], refine_iter=cfg["it"], precision=prec, output_upsample=True).eval()
         m.my_load_state_dict(sd)
         m = m.to(DEV)

@@ -67,6 +67,15 @@ class TorchOps:
         LayerNorm + two conv2d route on CPU."""
         return False
 
+    def mlp2(self, x, res, out, l0, l2, act):
+        """Returning False makes the schedule take the two conv2d launches on CPU."""
+        return False
+
+    def mlp2_reference(self, x, res, l0, l2, act):
+        h = _act(F.linear(x.float(), l0.w.float(), l0.b), act).to(x.dtype).float()
+        y = F.linear(h, l2.w.float(), l2.b)
+        return (y + res.float() if res is not None else y).to(x.dtype)
+
     def ln_linear(self, z, lin, out):
         """Returning False makes the schedule take the LayerNorm + conv2d route on CPU."""
         return False
@@ -91,12 +100,16 @@ class TorchOps:
         out = torch.matmul(attn, v)                                             # (S,heads,N,d)
         o.copy_(out.transpose(1, 2).reshape(o.shape).to(o.dtype))
         if pesum is not None:
-            px, py, h, w = pe
+            px, py, h, w = pe[:4]
             ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
             xs, ys = xs.reshape(-1).to(px.device), ys.reshape(-1).to(px.device)
             full = 0.5 * torch.cat([px[xs[:, None] - xs[None, :] + w - 1], py[ys[:, None] - ys[None, :] + h - 1]], 2)
             ps = torch.einsum("bnij,ijc->bnic", attn, full)                     # (S,heads,N,32)
             pesum.copy_(ps.transpose(1, 2).to(pesum.dtype))
+
+    def row_corr_tc(self, f, gamma, beta, cv):
+        """Returning False makes the schedule take the layernorm + row_corr route on CPU."""
+        return False
 
     def row_corr(self, f, cv):
         B = cv.shape[0]

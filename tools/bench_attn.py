@@ -16,7 +16,10 @@ SHAPES = [("1/4  scan-line",    512, 304, 1,    256, True),
           ("1/32 global 2-D",   2,   1216, 8,   64,  True),
           ("1/32 2-D batch 2",  4,   1216, 8,   64,  True),
           ("1/32 2-D batch 4",  8,   1216, 8,   64,  True),
-          ("1/32 2-D batch 8",  16,  1216, 8,   64,  True)]
+          ("1/32 2-D batch 8",  16,  1216, 8,   64,  True),
+          ("1/4  b8 scan-line", 4096, 304, 1,   256, True),
+          ("1/8  b8 scan-line", 2048, 152, 2,   128, True),
+          ("1/32 2-D b8 PE",    16,  1216, 8,   64,  False)]
 
 
 def timeit(fn, reps=20):
@@ -39,7 +42,11 @@ def main():
         C = heads * d
         qkv = torch.randn((1, S, N, 3 * C), generator=g).cuda().half()
         o = torch.empty((1, S, N, C), dtype=torch.float16, device="cuda")
-        t = timeit(lambda: ops.attention(qkv, o, S, N, heads, S // 2 if cross else 0))
+        pe = pesum = None
+        if name.endswith("PE"):
+            pe = ops.pe_tables(32, 38, torch.device("cuda"))
+            pesum = torch.empty((S, N, heads, 32), dtype=torch.float16, device="cuda")
+        t = timeit(lambda: ops.attention(qkv, o, S, N, heads, S // 2 if cross else 0, pe, pesum))
         flops = 4.0 * S * heads * N * N * d
         byts = qkv.numel() * 2 + o.numel() * 2
         print(f"{name:18s} S={S:4d} N={N:5d} h={heads} d={d:3d}  {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s  {byts / t / 1e3:7.1f} GB/s", flush=True)
