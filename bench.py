@@ -203,6 +203,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
 
     model = S2M2(C, 1, NTR, use_positivity=True, refine_iter=3, precision=args.precision).eval()
+    model.auto_graph = False          # the runtime below owns the captured graphs
     if rank == 0:
         model.my_load_state_dict(random_state_dict(C, NTR, 0))
     model = model.to(dev)

@@ -208,6 +208,17 @@ int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float*
  * interpolated x2 before the softmax, neighbourhood nearest x2, disparity doubled. */
 int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
                       int32_t upsample2, void* stream);
+/* The same filter writing only the centre window (crop_h x crop_w) of the padded frame = image_crop (image_utils.py:66-96) fused
+ * into the last kernel of the forward: out = three dense (B, crop_h, crop_w) fp32 maps [disparity | occlusion | confidence]. */
+int s2m2b200_filter1x_crop(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, int32_t crop_h,
+                           int32_t crop_w, float* out, void* stream);
+/* image_pad (image_utils.py:27-63; called by run_stereo_matching, model_utils.py:72-73) on the device: centre padding of a
+ * (B,3,H,W) uint8 / fp32 image to multiples of `factor`, the padding filled with the reference's blurred copy
+ * (adaptive_avg_pool2d to (H/factor, W/factor) of the zero-padded image, bilinear back up), the original pasted over it.
+ * out: (B,3,Hn,Wn) fp32, work: 3*B*(H/factor)*(W/factor) floats of device scratch. */
+int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int32_t W, int32_t factor, float* out, float* work,
+                       void* stream);
+
 
 const char* s2m2b200_last_error(void);
 /* Version / capability string, e.g. "s2m2b200 0.1 sm_100a tcgen05". */

@@ -5,6 +5,21 @@ Only tests/ may import this.  Each function cites the reference lines it follows
 import torch
 
 
+def image_pad(img: torch.Tensor, factor: int = 32) -> torch.Tensor:
+    """image_utils.py:27-63: centre zero-padding to multiples of ``factor`` (floor(pad/2) in front), the frame then replaced by
+    adaptive_avg_pool2d(padded, [H // factor, W // factor]) -> bilinear up to the padded size, and the original pasted back."""
+    import math
+
+    import torch.nn.functional as F
+    H, W = img.shape[-2:]
+    Hn, Wn = math.ceil(H / factor) * factor, math.ceil(W / factor) * factor
+    ph, pw = Hn - H, Wn - W
+    x = F.pad(img.float(), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), "constant", 0)
+    out = F.interpolate(F.adaptive_avg_pool2d(x, output_size=[H // factor, W // factor]), size=[Hn, Wn], mode="bilinear")
+    out[:, :, ph // 2: ph // 2 + H, pw // 2: pw // 2 + W] = img.float()
+    return out
+
+
 def image_crop(img: torch.Tensor, img_shape):
     """image_utils.py:66-96: centre crop of the last two dims, floor(d/2) dropped in front, the rest behind."""
     H, W = img.shape[-2:]

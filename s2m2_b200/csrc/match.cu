@@ -222,17 +222,19 @@ __global__ void upsample4x_kernel(const float* __restrict__ disp, const float* _
   }
 }
 
+// (y0, x0, Hc, Wc): the output window — image_crop (image_utils.py:66-96) fused into the last kernel of the forward: only the
+// un-padded pixels are filtered and written, as three dense (B, Hc, Wc) maps.  The full frame is y0 = x0 = 0, Hc = H, Wc = W.
 __global__ void filter1x_kernel(const float4* __restrict__ up, const float* __restrict__ logits, int lld, int B, int H, int W,
-                                float* __restrict__ out) {
+                                float* __restrict__ out, int y0, int x0, int Hc, int Wc) {
   pdl_sync();
-  const long long total = (long long)B * H * W;
+  const long long total = (long long)B * Hc * Wc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % W);
-    long long t = i / W;
-    int Y = (int)(t % H);
-    long long b = t / H;
+    int X = (int)(i % Wc) + x0;
+    long long t = i / Wc;
+    int Y = (int)(t % Hc) + y0;
+    long long b = t / Hc;
     float wt[9];
-    softmax9(logits + i * lld, wt);
+    softmax9(logits + ((b * H + Y) * W + X) * lld, wt);
     float d = 0.f, o = 0.f, c = 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy)
@@ -343,6 +345,70 @@ __global__ void disparity_to_points_kernel(const float* __restrict__ disp, const
     valid[i] = ok ? 1 : 0;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// image_pad (image_utils.py:27-63), the pre-processing of run_stereo_matching (model_utils.py:72-73), on the device:
+// centre zero-padding to multiples of `factor`, the padding then filled with a blurred copy of the padded image
+// (adaptive_avg_pool2d to (H/factor, W/factor) -> bilinear back up, align_corners=False), the original pasted over it.
+//   kernel 1  pad_pool_kernel   one warp per (image, channel, pooled cell): mean of its adaptive window of the zero-padded image
+//   kernel 2  pad_fill_kernel   every output pixel: inside -> the input pixel, padding -> bilinear sample of the pooled grid
+// Input uint8 or fp32 (the same integer values either way), output fp32 (B,3,Hn,Wn).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pad_pool_kernel(const T* __restrict__ img, int BC, int H, int W, int Hn, int Wn, int hs, int ws, int Ho, int Wo,
+                                float* __restrict__ pooled) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long cells = (long long)BC * Ho * Wo;
+  for (long long c = warp; c < cells; c += nw) {
+    const int ox = (int)(c % Wo);
+    const long long t = c / Wo;
+    const int oy = (int)(t % Ho);
+    const long long bc = t / Ho;
+    // adaptive windows of the PADDED image: [floor(o*In/Out), ceil((o+1)*In/Out))
+    const int y0 = (int)(((long long)oy * Hn) / Ho), y1 = (int)((((long long)oy + 1) * Hn + Ho - 1) / Ho);
+    const int x0 = (int)(((long long)ox * Wn) / Wo), x1 = (int)((((long long)ox + 1) * Wn + Wo - 1) / Wo);
+    const int ww = x1 - x0, n = (y1 - y0) * ww;
+    float s = 0.f;
+    for (int k = lane; k < n; k += 32) {
+      const int yy = y0 + k / ww - hs, xx = x0 + k % ww - ws;          // coordinates in the un-padded image
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) s += (float)img[(bc * H + yy) * W + xx];
+    }
+    s = warp_sum(s);
+    if (lane == 0) pooled[c] = s / (float)n;
+  }
+}
+
+template <typename T>
+__global__ void pad_fill_kernel(const T* __restrict__ img, const float* __restrict__ pooled, int BC, int H, int W, int Hn, int Wn, int hs,
+                                int ws, int Ho, int Wo, float* __restrict__ out) {
+  pdl_sync();
+  const long long total = (long long)BC * Hn * Wn;
+  const float sy = (float)Ho / (float)Hn, sx = (float)Wo / (float)Wn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Wn);
+    const long long t = i / Wn;
+    const int Y = (int)(t % Hn);
+    const long long bc = t / Hn;
+    const int yy = Y - hs, xx = X - ws;
+    float v;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      v = (float)img[(bc * H + yy) * W + xx];
+    } else {   // F.interpolate(bilinear, align_corners=False): src = (dst + .5) * scale - .5, clamped at 0
+      const float fy = fmaxf(((float)Y + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf(((float)X + 0.5f) * sx - 0.5f, 0.f);
+      const int iy = (int)fy, ix = (int)fx;
+      const int iy1 = min(iy + 1, Ho - 1), ix1 = min(ix + 1, Wo - 1);
+      const float ty = fy - (float)iy, tx = fx - (float)ix;
+      const float* g = pooled + bc * Ho * Wo;
+      const float a = g[iy * Wo + ix], b2 = g[iy * Wo + ix1], c2 = g[iy1 * Wo + ix], d2 = g[iy1 * Wo + ix1];
+      v = (1.f - ty) * ((1.f - tx) * a + tx * b2) + ty * ((1.f - tx) * c2 + tx * d2);
+    }
+    out[i] = v;
+  }
+}
+
 }  // namespace s2m2
 
 namespace s2m2 {
@@ -399,8 +465,46 @@ int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, i
   }
   long long n = (long long)B * H * W;
   long long g = (n + 255) / 256;
-  launch_k(filter1x_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, (const float4*)up, logits, logits_ld, B, H, W, out);
+  launch_k(filter1x_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, (const float4*)up, logits, logits_ld, B, H, W, out,
+           0, 0, H, W);
   S2M2_LAUNCH_OK("filter1x");
+  return 0;
+}
+
+int s2m2b200_filter1x_crop(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, int32_t crop_h,
+                           int32_t crop_w, float* out, void* stream) {
+  S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "filter1x_crop: up must be 16-byte aligned, logits_ld >= 9");
+  S2M2_CHECK(crop_h > 0 && crop_w > 0 && crop_h <= H && crop_w <= W, "filter1x_crop: bad crop %dx%d of %dx%d", crop_h, crop_w, H, W);
+  const int y0 = (H - crop_h) / 2, x0 = (W - crop_w) / 2;          // image_crop drops floor(d/2) rows / columns in front
+  long long n = (long long)B * crop_h * crop_w;
+  long long g = (n + 255) / 256;
+  launch_k(filter1x_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, (const float4*)up, logits, logits_ld, B, H, W, out,
+           y0, x0, crop_h, crop_w);
+  S2M2_LAUNCH_OK("filter1x_crop");
+  return 0;
+}
+
+int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int32_t W, int32_t factor, float* out, float* work,
+                       void* stream) {
+  S2M2_CHECK(factor > 0 && H >= factor && W >= factor, "image_pad: the image must be at least factor x factor");
+  const int Hn = (H + factor - 1) / factor * factor, Wn = (W + factor - 1) / factor * factor;
+  const int hs = (Hn - H) / 2, ws = (Wn - W) / 2;                   // image_utils.py:47-52: floor(pad/2) in front
+  const int Ho = H / factor, Wo = W / factor;                        // image_utils.py:54 (the UN-padded size / factor)
+  const int BC = B * 3;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long cells = (long long)BC * Ho * Wo, total = (long long)BC * Hn * Wn;
+  const int gp = (int)((cells * 32 + 255) / 256 > 148 * 32 ? 148 * 32 : (cells * 32 + 255) / 256);
+  const int gf = (int)((total + 255) / 256 > 148 * 64 ? 148 * 64 : (total + 255) / 256);
+  if (is_u8) {
+    launch_k(pad_pool_kernel<uint8_t>, gp, 256, 0, s, (const uint8_t*)img, BC, H, W, Hn, Wn, hs, ws, Ho, Wo, work);
+    S2M2_LAUNCH_OK("pad_pool");
+    launch_k(pad_fill_kernel<uint8_t>, gf, 256, 0, s, (const uint8_t*)img, (const float*)work, BC, H, W, Hn, Wn, hs, ws, Ho, Wo, out);
+  } else {
+    launch_k(pad_pool_kernel<float>, gp, 256, 0, s, (const float*)img, BC, H, W, Hn, Wn, hs, ws, Ho, Wo, work);
+    S2M2_LAUNCH_OK("pad_pool");
+    launch_k(pad_fill_kernel<float>, gf, 256, 0, s, (const float*)img, (const float*)work, BC, H, W, Hn, Wn, hs, ws, Ho, Wo, out);
+  }
+  S2M2_LAUNCH_OK("pad_fill");
   return 0;
 }
 

@@ -21,57 +21,63 @@ namespace s2m2 {
 using namespace tc;
 
 // ---- kernel 1: LayerNorm + hi/lo split -----------------------------------------------------------------------------
-// one warp per pixel; C % 8 == 0, C <= 512.  planes: [2][npix][C] fp16 (hi plane, then lo plane)
+// 8 lanes per pixel (4 pixels per warp in flight: the statistics need 3 shuffle steps and every lane keeps up to four 16-byte
+// loads outstanding); C % 64 == 0, C <= 256.  planes: [2][npix][C] fp16 (hi plane, then lo plane)
 __global__ void __launch_bounds__(256) ln_split_kernel(const __half* __restrict__ x, long long x_ld, long long npix, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        __half* __restrict__ planes) {
   pdl_sync();
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const int nu = C >> 3;                                  // 16-byte units per pixel
-  for (long long pix = warp0; pix < npix; pix += nwarps) {
+  const int sub = threadIdx.x & 7;                           // lane within the pixel's group of 8
+  const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long ng = ((long long)gridDim.x * blockDim.x) >> 3;
+  const int nt = C >> 6;                                      // 16-byte units per lane: C / 8 units over 8 lanes
+  const long long last = npix - 1;
+  for (long long pg = g0; pg < ((npix + 3) / 4) * 4; pg += ng) {   // whole warps stay in the loop (shuffles below)
+    const bool live = pg <= last;
+    const long long pix = live ? pg : last;
     const __half* row = x + pix * x_ld;
-    float v[2][8];
+    float v[4][8];
     float s = 0.f;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int un = lane + 32 * t;
-      if (un < nu) {
-        const uint4 raw = *(const uint4*)(row + un * 8);
+    for (int t = 0; t < 4; ++t)
+      if (t < nt) {
+        const uint4 raw = *(const uint4*)(row + (sub + 8 * t) * 8);
         const __half2* h = (const __half2*)&raw;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[t][2 * i] = f.x; v[t][2 * i + 1] = f.y; s += f.x + f.y; }
       }
-    }
-    s = warp_sum(s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
     const float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (lane + 32 * t < nu) {
+    for (int t = 0; t < 4; ++t)
+      if (t < nt) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const float d = v[t][i] - mean; q += d * d; }
       }
-    q = warp_sum(q);
+    q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
     const float rstd = rsqrtf(q / (float)C + 1e-5f);
+    if (live) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int un = lane + 32 * t;
-      if (un < nu) {
-        __half2 hi[4], lo[4];
+      for (int t = 0; t < 4; ++t)
+        if (t < nt) {
+          const int un = sub + 8 * t;
+          const float4 g0v = __ldg((const float4*)(gamma + un * 8)), g1v = __ldg((const float4*)(gamma + un * 8 + 4));
+          const float4 b0v = __ldg((const float4*)(beta + un * 8)), b1v = __ldg((const float4*)(beta + un * 8 + 4));
+          const float gg[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
+          const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+          __half2 hi[4], lo[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = un * 8 + 2 * i;
-          const float a = (v[t][2 * i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-          const float b = (v[t][2 * i + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-          const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-          hi[i] = __halves2half2(ah, bh);
-          lo[i] = __floats2half2_rn(a - __half2float(ah), b - __half2float(bh));
+          for (int i = 0; i < 4; ++i) {
+            const float a = (v[t][2 * i] - mean) * rstd * gg[2 * i] + bb[2 * i];
+            const float b = (v[t][2 * i + 1] - mean) * rstd * gg[2 * i + 1] + bb[2 * i + 1];
+            const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+            hi[i] = __halves2half2(ah, bh);
+            lo[i] = __floats2half2_rn(a - __half2float(ah), b - __half2float(bh));
+          }
+          *(uint4*)(planes + pix * C + un * 8) = *(uint4*)&hi[0];
+          *(uint4*)(planes + (npix + pix) * C + un * 8) = *(uint4*)&lo[0];
         }
-        *(uint4*)(planes + pix * C + un * 8) = *(uint4*)&hi[0];
-        *(uint4*)(planes + (npix + pix) * C + un * 8) = *(uint4*)&lo[0];
-      }
     }
   }
 }
@@ -242,7 +248,7 @@ using namespace s2m2;
 
 // Scratch bytes for the hi / lo planes of s2m2b200_row_corr (0 = shape not taken by the tcgen05 path).
 extern "C" int64_t s2m2b200_row_corr_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t C) {
-  if (C % 64 || C > 256 || w % 4 || w < 32 || w > 512) return 0;
+  if (C % 64 || C > 256 || w % 4 || w < 32 || w > 512) return 0;   // (ln_split: C % 64; rowcorr: <= 4 k-blocks, <= 4 column chunks)
   return (int64_t)2 * 2 * B * h * w * C * 2;
 }
 
@@ -255,13 +261,13 @@ extern "C" int s2m2b200_row_corr(const S2m2Tensor* f, const float* gamma, const 
   if (f->dtype != S2M2_F16 || f->N % 2 || !work) return 1;
   const int64_t need = s2m2b200_row_corr_workspace_bytes(B, h, w, C);
   if (need == 0 || work_bytes < need) return 1;
-  if (f->ld % 8 || !aligned(f->ptr, 16) || !aligned(work, 128) || !aligned(cv, 16) || !gamma || !beta) return 1;
+  if (f->ld % 8 || !aligned(f->ptr, 16) || !aligned(work, 128) || !aligned(cv, 16) || !gamma || !beta || !aligned(gamma, 16) || !aligned(beta, 16)) return 1;
   if (!tc::device_ok()) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   const long long npix = (long long)f->N * h * w;
   {
-    const long long warps = npix;
-    const int blocks = (int)((warps + 7) / 8 < 148 * 16 ? (warps + 7) / 8 : 148 * 16);
+    const long long blocks_needed = (npix + 31) / 32;                 // 32 pixels per 256-thread block and iteration
+    const int blocks = (int)(blocks_needed < 148 * 16 ? blocks_needed : 148 * 16);
     launch_k(ln_split_kernel, blocks, 256, 0, s, (const __half*)f->ptr, (long long)f->ld, npix, C, gamma, beta, (__half*)work);
     S2M2_LAUNCH_OK("ln_split");
   }

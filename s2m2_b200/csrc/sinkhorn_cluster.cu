@@ -26,9 +26,9 @@ namespace cg = cooperative_groups;
 
 namespace s2m2 {
 
-constexpr int SKC_THREADS = 512;
-constexpr int SKC_NW = SKC_THREADS / 32;
-constexpr int SKC_SLOTS = SKC_NW / 2;                 // cross-warp combine buffers (two rounds)
+// Threads per CTA are a template parameter (512 by default; S2M2_SK_NT=256 selects 8-warp CTAs, up to four per SM).  The sweeps
+// are short and every half-iteration ends in block- and cluster-wide barriers after a global-memory load phase: the ncu stall
+// samples are barrier / wait, not the exponentials (profiles/r2_dispinit.md).
 constexpr float SKC_L2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float skc_ex2(float x) {
@@ -50,6 +50,38 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
   m = M;
 }
 
+// One row's contribution to the column sums / its own row sum, specialised on the number NCH of 32-column chunks the row really
+// has: the rows of the triangular (positivity-masked) matrix are i + 1 entries long, and a loop unrolled to the full width with
+// predicates issues (predicated-off) instructions for all of it.
+template <int NCH>
+__device__ __forceinline__ void skc_col_row(const float* __restrict__ rowp, float ui, const float* mj, float* cs, int lane, int jend) {
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int j = lane + 32 * k;
+    if (k < NCH - 1 || j < jend) cs[k] += skc_ex2(((rowp[j] + ui) - mj[k]) * SKC_L2E);
+  }
+}
+template <int NCH>
+__device__ __forceinline__ float skc_row_sum(const float* __restrict__ rowp, const float* __restrict__ v, float mi, int lane, int jend) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int j = lane + 32 * k;
+    if (k < NCH - 1 || j < jend) {
+      const float e = skc_ex2(((rowp[j] + v[j]) - mi) * SKC_L2E);
+      if (k & 1) s1 += e; else s0 += e;
+    }
+  }
+  return s0 + s1;
+}
+#define SKC_DISPATCH(nch, CALL)                                                                                         \
+  switch (nch) {                                                                                                          \
+    case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break;       \
+    case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break;     \
+    case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; case 15: CALL(15); break; \
+    case 16: CALL(16); break; case 17: CALL(17); break; case 18: CALL(18); break; case 19: CALL(19); break; default: CALL(20); break; \
+  }
+
 struct SkcP {
   const float* cv;
   float *disp, *conf, *occ;
@@ -60,8 +92,10 @@ struct SkcP {
 };
 
 // NC = column registers per lane: 32 * NC >= w + 1
-template <int NC>
-__global__ void __launch_bounds__(SKC_THREADS, (NC <= 10 ? 2 : 1)) sinkhorn_cluster_kernel(const SkcP p) {
+template <int NC, int SKC_THREADS>
+__global__ void __launch_bounds__(SKC_THREADS, (NC <= 10 ? (SKC_THREADS <= 256 ? 4 : 2) : 1)) sinkhorn_cluster_kernel(const SkcP p) {
+  constexpr int SKC_NW = SKC_THREADS / 32;
+  constexpr int SKC_SLOTS = SKC_NW / 2;                 // cross-warp combine buffers (two rounds)
   pdl_sync();
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks();
@@ -178,49 +212,97 @@ __global__ void __launch_bounds__(SKC_THREADS, (NC <= 10 ? 2 : 1)) sinkhorn_clus
     __syncthreads();
   };
 
-  // row sweep: u[i] = log_mu[i] - LSE_j (A(i,j) + v[j])  for this CTA's rows, all-gathered through DSMEM
-  auto row_sweep = [&]() {
+  // ---- bound-shifted sweeps.  After a row update  A(i,j) + u[i] + v[j] <= log_mu[i] <= log(1/2)  for every entry (each term of a
+  // normalised row is at most the row's log-mass), so  A(i,j) + u[i] <= log(1/2) - v[j] =: m_j  is a safe shift for column j of the
+  // NEXT column sweep — and symmetrically  A(i,j) + v[j] <= log(1/2) - u[i]  for the next row sweep.  With the shift known in
+  // advance the log-sum-exp is a single pass of INDEPENDENT exponentials (no running max, no dependent rescaling chain):
+  //     LSE = m + log(sum exp(x - m)),   sum in [~1/(2w e), 1]  — far from under- / overflow.
+  // Only the very first column sweep (u = v = 0, no bound yet) runs the online (max, sum) version above.
+  auto col_sweep_bound = [&]() {
+    float cs[NC], mj[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int j = lane + 32 * k;
+      cs[k] = 0.f;
+      mj[k] = log_m_dust - (j < W1 ? v[j] : 0.f);
+    }
     for (int q = wid; q < nrows; q += SKC_NW) {
       int i, jend;
       const float* rowp;
       if (!row_of(q, i, rowp, jend)) continue;
-      float m = -3.0e38f, s = 0.f;
+      const float ui = u[i];
+      const int nch = (jend + 31) >> 5;                   // warp-uniform
+#define SKC_CALL(N) if (N <= NC) skc_col_row<(N <= NC ? N : 1)>(rowp, ui, mj, cs, lane, jend)
+      SKC_DISPATCH(nch, SKC_CALL)
+#undef SKC_CALL
+    }
+    // dust-bin column j = w: sum_{i = 0..w} exp(u[i] - m_w), by the last warp of every CTA for itself, before the cluster barrier
+    if (wid == SKC_NW - 1) {
+      const float mw = log_m_dust - v[w];
+      float s0 = 0.f;
+      for (int i = lane; i < W1; i += 32) s0 += skc_ex2((u[i] - mw) * SKC_L2E);
+      s0 = warp_sum(s0);
+      if (lane == 0) v[w] = log_m_dust - (mw + logf(fmaxf(s0, 1e-30f)));
+    }
+    if (wid >= SKC_SLOTS) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        if (32 * k < jend) {
-          const int j = lane + 32 * k;
-          if (j < jend) lse_push(m, s, rowp[j] + v[j]);
-        }
-      }
-      if (lane == 0) lse_push(m, s, v[w]);              // dust-bin column: A = 0
+      for (int k = 0; k < NC; ++k) ws[(wid - SKC_SLOTS) * 32 * NC + 32 * k + lane] = cs[k];
+    }
+    __syncthreads();
+    if (wid < SKC_SLOTS) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-        lse_merge(m, s, m2, s2);
-      }
+      for (int k = 0; k < NC; ++k) ws[wid * 32 * NC + 32 * k + lane] += cs[k];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < w; j += SKC_THREADS) {
+      float sj = ws[j];
+#pragma unroll
+      for (int ww = 1; ww < SKC_SLOTS; ++ww) sj += ws[ww * 32 * NC + j];
+      for (int c = 0; c < CS; ++c) cluster.map_shared_rank(ps, c)[(size_t)crank * W1 + j] = sj;
+    }
+    cluster.sync();
+    for (int j = threadIdx.x; j < w; j += SKC_THREADS) {
+      const float m = log_m_dust - v[j];
+      float sj = skc_ex2((u[w] - m) * SKC_L2E);          // the dust-bin row i = w: A = 0
+      for (int c = 0; c < CS; ++c) sj += ps[(size_t)c * W1 + j];
+      v[j] = log_m_in - (m + logf(fmaxf(sj, 1e-30f)));
+    }
+    __syncthreads();
+  };
+  auto row_sweep_bound = [&]() {
+    for (int q = wid; q < nrows; q += SKC_NW) {
+      int i, jend;
+      const float* rowp;
+      if (!row_of(q, i, rowp, jend)) continue;
+      const float mi = log_m_dust - u[i];
+      const int nch = (jend + 31) >> 5;
+      float sr = 0.f;
+#define SKC_CALL(N) if (N <= NC) sr = skc_row_sum<(N <= NC ? N : 1)>(rowp, v, mi, lane, jend)
+      SKC_DISPATCH(nch, SKC_CALL)
+#undef SKC_CALL
+      if (lane == 0) sr += skc_ex2((v[w] - mi) * SKC_L2E);   // dust-bin column: A = 0
+      sr = warp_sum(sr);
       if (lane == 0) {
-        const float ui = log_m_in - (m + logf(fmaxf(s, 1e-30f)));
+        const float ui = log_m_in - (mi + logf(fmaxf(sr, 1e-30f)));
         for (int c = 0; c < CS; ++c) cluster.map_shared_rank(u, c)[i] = ui;
       }
     }
-    // dust-bin row i = w: A = 0 everywhere -> LSE_j v[j] over j = 0..w; every CTA evaluates it for itself (same inputs, same order)
-    if (wid == SKC_NW - 1) {
-      float m = -3.0e38f, s = 0.f;
-      for (int j = lane; j < W1; j += 32) lse_push(m, s, v[j]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-        lse_merge(m, s, m2, s2);
-      }
-      if (lane == 0) u[w] = log_m_dust - (m + logf(fmaxf(s, 1e-30f)));
+    if (wid == SKC_NW - 1) {   // dust-bin row i = w: A = 0 everywhere
+      const float mw = log_m_dust - u[w];
+      float s0 = 0.f;
+      for (int j = lane; j < W1; j += 32) s0 += skc_ex2((v[j] - mw) * SKC_L2E);
+      s0 = warp_sum(s0);
+      if (lane == 0) u[w] = log_m_dust - (mw + logf(fmaxf(s0, 1e-30f)));
     }
     cluster.sync();
   };
 
   // (the first column sweep runs with u = 0: v = log_nu - LSE_i A, submodules.py:172)
-  for (int it = 0; it < p.iters; ++it) {
-    col_sweep();
-    row_sweep();
+  col_sweep();
+  row_sweep_bound();        // u = 0 so far: A(i,j) + v[j] <= log_nu[j] - 0 holds after the first column normalisation
+  for (int it = 1; it < p.iters; ++it) {
+    col_sweep_bound();
+    row_sweep_bound();
   }
 
   // ---- probabilities of this CTA's rows: row sum (occ), first arg-max, 5 taps around it (submodules.py:198-241)
@@ -276,10 +358,10 @@ static void skc_geometry(int w, int pos, int CS, int& ld, int& nlines) {
     nlines = (w + CS - 1) / CS;
   }
 }
-static size_t skc_smem(int w, int pos, int CS, int NC) {
+static size_t skc_smem(int w, int pos, int CS, int NC, int NT) {
   int ld, nlines;
   skc_geometry(w, pos, CS, ld, nlines);
-  return sizeof(float) * ((size_t)nlines * ld + 2 * (size_t)(w + 1) + 2 * (size_t)CS * (w + 1) + 2 * (size_t)SKC_SLOTS * 32 * NC);
+  return sizeof(float) * ((size_t)nlines * ld + 2 * (size_t)(w + 1) + 2 * (size_t)CS * (w + 1) + 2 * (size_t)(NT / 64) * 32 * NC);
 }
 
 // 0 = launched; 1 = this width is not taken by the cluster kernel (the caller runs the streaming kernel); < 0 = error
@@ -288,33 +370,37 @@ int sinkhorn_cluster_launch(const float* cv, int B, int h, int w, float* disp, f
   if (w + 1 > 640 || w < 8) return 1;
   const int NC = (w + 1 + 31) / 32 <= 10 ? 10 : 20;
   static const int cs_env = getenv("S2M2_SK_CS") ? atoi(getenv("S2M2_SK_CS")) : 0;
-  constexpr size_t SMEM_MAX = 220 * 1024, SMEM_TWO = 112 * 1024;   // two CTAs per SM when a share fits half the shared memory
+  static const int nt_env = getenv("S2M2_SK_NT") ? atoi(getenv("S2M2_SK_NT")) : 0;
+  const int NT = (NC == 10 && nt_env == 256) ? 256 : 512;      // measured at L, batch 8: 512 threads x 4-CTA clusters 1.29 ms, 256 threads 1.38-1.41 ms
+  constexpr size_t SMEM_MAX = 220 * 1024;
+  // the smallest cluster whose share lets at least `want` CTAs live on one SM (227 KB): more co-resident CTAs hide the barriers
+  const size_t want_bytes = NT == 256 ? 56 * 1024 : 112 * 1024;
   int CS = 0;
-  if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) {
-    if (skc_smem(w, pos, cs_env, NC) <= SMEM_MAX) CS = cs_env;
-  }
+  if ((cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) && skc_smem(w, pos, cs_env, NC, NT) <= SMEM_MAX) CS = cs_env;
   if (!CS)
     for (int c = 1; c <= 8 && !CS; c *= 2)
-      if (skc_smem(w, pos, c, NC) <= SMEM_TWO) CS = c;
+      if (skc_smem(w, pos, c, NC, NT) <= want_bytes) CS = c;
   if (!CS)
     for (int c = 1; c <= 8 && !CS; c *= 2)
-      if (skc_smem(w, pos, c, NC) <= SMEM_MAX) CS = c;
+      if (skc_smem(w, pos, c, NC, NT) <= SMEM_MAX) CS = c;
   if (!CS) return 1;
-  const size_t smem = skc_smem(w, pos, CS, NC);
+  const size_t smem = skc_smem(w, pos, CS, NC, NT);
   SkcP p{};
   p.cv = cv; p.disp = disp; p.conf = conf; p.occ = occ; p.amax = amax; p.w = w; p.pos = pos; p.iters = iters;
   skc_geometry(w, pos, CS, p.lines_ld, p.nlines_max);
-  auto kernel = NC == 10 ? sinkhorn_cluster_kernel<10> : sinkhorn_cluster_kernel<20>;
-  static bool attr[S2M2_MAX_DEVICES][2] = {{false}};
+  void (*kernel)(const SkcP) = NC == 10 ? (NT == 256 ? sinkhorn_cluster_kernel<10, 256> : sinkhorn_cluster_kernel<10, 512>)
+                                        : sinkhorn_cluster_kernel<20, 512>;
+  const int ki = NC == 10 ? (NT == 256 ? 0 : 1) : 2;
+  static bool attr[S2M2_MAX_DEVICES][3] = {{false}};
   const int di = current_device_index();
-  if (!attr[di][NC == 20]) {
+  if (!attr[di][ki]) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
     S2M2_CHECK(e == cudaSuccess, "sinkhorn_cluster: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr[di][NC == 20] = true;
+    attr[di][ki] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((long long)B * h * CS));
-  cfg.blockDim = dim3(SKC_THREADS);
+  cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[2];

@@ -61,10 +61,25 @@ class S2M2(nn.Module):
         self._packed = None        # packed weights (device, precision) — rebuilt when parameters move/change
         self._packed_key = None
         self.taps: Optional[dict] = None   # set to a dict to collect stage outputs (tests)
+        import os
+        self.auto_graph = os.environ.get("S2M2_AUTO_GRAPH", "1") != "0"   # replay a captured CUDA graph on repeated same-shape calls
+        self.auto_graph_slots = int(os.environ.get("S2M2_AUTO_GRAPH_SLOTS", "2"))
+        self._graphs = {}
 
     # ---- nn.Module surface -------------------------------------------------------------------
-    def state_dict(self, *args, **kwargs):  # reference key names
-        return {name: self._p[name.replace(".", "/")].data for name, _ in self._spec}
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """nn.Module.state_dict under the REFERENCE key names (the parameters live in a flat ParameterDict because '.' is not
+        allowed in parameter names); honours ``destination`` / ``prefix`` / ``keep_vars`` like torch."""
+        if args:   # legacy positional form (destination, prefix, keep_vars)
+            destination = args[0] if len(args) > 0 else destination
+            prefix = args[1] if len(args) > 1 else prefix
+            keep_vars = args[2] if len(args) > 2 else keep_vars
+        from collections import OrderedDict
+        out = OrderedDict() if destination is None else destination
+        for name, _ in self._spec:
+            p = self._p[name.replace(".", "/")]
+            out[prefix + name] = p if keep_vars else p.detach()
+        return out
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         own = {name for name, _ in self._spec}
@@ -80,7 +95,9 @@ class S2M2(nn.Module):
                 p = self._p[name.replace(".", "/")]
                 p.data = t.detach().to(device=p.device, dtype=torch.float32).clone()
         self._packed = None
-        return missing, unexpected
+        self._graphs = {}
+        from torch.nn.modules.module import _IncompatibleKeys
+        return _IncompatibleKeys(missing, unexpected)
 
     def my_load_state_dict(self, state_dict):
         """Tolerant load, same behaviour as s2m2.py:69-78: shape-mismatched keys are skipped with a print."""
@@ -95,6 +112,7 @@ class S2M2(nn.Module):
 
     def _apply(self, fn, recurse=True):
         self._packed = None
+        self._graphs = {}
         return super()._apply(fn, recurse)
 
     # ---- weight packing ------------------------------------------------------------------------
@@ -429,8 +447,8 @@ class S2M2(nn.Module):
         self.ops.upsample2x(t, u)
         return u
 
-    def _unet(self, z, p, pe=None, tap=None):
-        """Unet.forward (unet.py:65-112)."""
+    def _unet(self, z, p, pe=None, tap=None, out0=None):
+        """Unet.forward (unet.py:65-112).  ``out0``: optional destination view of the 1/4-resolution decoder output."""
         z0 = self._convblock(z, p["enc0"])
         z1 = self._convblock(self._down(z0, p["down0"]), p["enc1"])
         z2 = self._convblock(self._down(z1, p["down1"]), p["enc2"])
@@ -443,7 +461,7 @@ class S2M2(nn.Module):
             z3 = self._global_block(z3, bp, False)
         z2n = self._convblock(self._fusion(z2, self._up(z3, p["up2"]), p["cat2"]), p["dec2"])
         z1n = self._convblock(self._fusion(z1, self._up(z2n, p["up1"]), p["cat1"]), p["dec1"])
-        z0n = self._convblock(self._fusion(z0, self._up(z1n, p["up0"]), p["cat0"]), p["dec0"])
+        z0n = self._convblock(self._fusion(z0, self._up(z1n, p["up0"]), p["cat0"]), p["dec0"], out=out0)
         return z0n, z1n, z2n, z3
 
     def _mrt(self, z0, z1, z2, z3, p):
@@ -465,8 +483,53 @@ class S2M2(nn.Module):
 
     # ---- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, img0: torch.Tensor, img1: torch.Tensor):
-        """(B,3,H,W) float [0,255] x2 -> disparity, occlusion, confidence, each (B,1,H,W) fp32 (s2m2.py:136-197)."""
+    def forward(self, img0: torch.Tensor, img1: torch.Tensor, crop_hw=None):
+        """(B,3,H,W) float [0,255] x2 -> disparity, occlusion, confidence, each (B,1,H,W) fp32 (s2m2.py:136-197).
+        ``crop_hw`` (not in the reference's signature; default None = the reference's behaviour): the un-padded image size —
+        the last kernel then writes only that centre window, i.e. image_crop (image_utils.py:66-96, the step
+        run_stereo_matching applies to each output, model_utils.py:89-91) is fused into it.
+
+        Repeated calls with the same (shape, dtype, crop) replay a CUDA graph captured on the second such call: the ~900 kernel
+        launches of one forward then cost one graph launch on the host — what the reference's caller
+        (run_stereo_matching's timing loop, model_utils.py:79-83; the calibration optimisers' ~100 calls, cem.py:55-72) sees
+        through the unchanged nn.Module surface.  ``model.auto_graph = False`` (or S2M2_AUTO_GRAPH=0) keeps every call eager."""
+        if (self.auto_graph and self.taps is None and img0.is_cuda and self.ops is not None and hasattr(self.ops, "lib")
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_graphed(img0, img1, crop_hw)
+        return self._forward_eager(img0, img1, crop_hw)
+
+    def _forward_graphed(self, img0, img1, crop_hw):
+        key = (tuple(img0.shape), img0.dtype, img1.dtype, str(img0.device), None if crop_hw is None else tuple(int(v) for v in crop_hw),
+               self.precision, self.use_positivity, self.refine_iter, self.output_upsample)
+        ent = self._graphs.get(key)
+        if ent is None:                       # first call at this shape: eager (it also packs weights / builds tables)
+            self._graphs[key] = {"n": 1}
+            while len(self._graphs) > self.auto_graph_slots:       # a captured graph pins its whole activation pool: keep few
+                self._graphs.pop(next(iter(self._graphs)))
+            return self._forward_eager(img0, img1, crop_hw)
+        if "graph" not in ent:                # second call: capture
+            if tuple(img0.shape) != tuple(img1.shape):
+                return self._forward_eager(img0, img1, crop_hw)
+            dev = img0.device
+            ent["in0"], ent["in1"] = torch.empty_like(img0, memory_format=torch.contiguous_format), torch.empty_like(img1, memory_format=torch.contiguous_format)
+            ent["in0"].copy_(img0); ent["in1"].copy_(img1)
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    out = self._forward_eager(ent["in0"], ent["in1"], crop_hw)
+            cur.wait_stream(side)
+            ent["graph"], ent["out"] = g, out
+            g.replay()
+            return tuple(t.clone() for t in out)
+        self._graphs[key] = self._graphs.pop(key)                  # most recently used last
+        ent["in0"].copy_(img0); ent["in1"].copy_(img1)
+        ent["graph"].replay()
+        return tuple(t.clone() for t in ent["out"])               # the graph's output buffers are overwritten by the next replay
+
+    def _forward_eager(self, img0: torch.Tensor, img1: torch.Tensor, crop_hw=None):
         if self.ops is None:
             from .ops import CudaOps
             self.ops = CudaOps()                      # raises if the library / GPU is missing: no fallback
@@ -553,7 +616,7 @@ class S2M2(nn.Module):
         self._c(self._c(fus, P["ctx0"], ACT_GELU), P["ctx2"], out=ctx0)
         self._tap("ctx0", ctx0)
         hx = ops.empty((B, h4, w4, 2 * C), adt, dev)                    # GRU state | GRU input
-        rhx = ops.empty((B, h4, w4, 2 * C), adt, dev)
+        rh = ops.empty((B, h4, w4, C), adt, dev)                        # r * h
         hidden = hx[..., :C]
         ops.unary(ctx0, hidden, ACT_TANH)
 
@@ -568,15 +631,13 @@ class S2M2(nn.Module):
             self._c(self._c(corr[..., 9:18], lr["cf20"], ACT_GELU), lr["cf22"], out=xcat[..., 160:224])
             self._c(self._c(small[..., 1:3], lr["co0"], ACT_GELU), lr["co2"], out=xcat[..., 224 + C:256 + C])
             x = self._c(self._c(xcat, lr["cat0"], ACT_GELU), lr["cat2"])
-            u = self._unet(x, lr["unet"])
             xin = hx[..., C:]
-            ops.copy_channels(u[0], xin)
-            ops.copy_channels(u[0], rhx[..., C:])
-            del u, x
+            self._unet(x, lr["unet"], out0=xin)          # the U-Net's last ConvBlock writes straight into the GRU input slot [h | x]
+            del x
             for zr, q in ((lr["zr1"], lr["q1"]), (lr["zr2"], lr["q2"])):     # ConvGRU (refinenet.py:22-36)
                 zrt = self._c(hx, zr, ACT_SIGMOID)
-                ops.mul(zrt[..., C:], hidden, rhx[..., :C])
-                qt = self._c(rhx, q, ACT_TANH)
+                ops.mul(zrt[..., C:], hidden, rh)
+                qt = self._c(rh, q, ACT_TANH, x2=xin)                       # conv over cat([r*h, x]) reads the two sources in place
                 ops.gru_update(zrt[..., :C], qt, hidden)                    # hidden = (1-z) h + z q, in place
             t = self._c(hidden, lr["upd0"], ACT_GELU)
             upd = self._c(t, lr["upd2"], out_dtype=f32)                    # [d disp | d conf logit | d occ logit | pad]
@@ -605,6 +666,13 @@ class S2M2(nn.Module):
         self._c(f2_0, u1["ctx"], out=m1in[..., 32:48])
         m1 = self._c(self._c(m1in, u1["c0"], ACT_RELU), u1["c2"], out_dtype=f32)
         sc = 2 if self.output_upsample else 1                            # s2m2.py:123-127,194-195
+        if crop_hw is not None and not self.output_upsample:
+            hc, wc = int(crop_hw[0]), int(crop_hw[1])
+            if not (0 < hc <= H and 0 < wc <= W):
+                raise ValueError(f"crop_hw {crop_hw} does not fit the {H}x{W} frame")
+            out = ops.empty((3, B, 1, hc, wc), f32, dev)
+            ops.filter1x_crop(up, m1, out, (hc, wc))
+            return out[0], out[1], out[2]
         out = ops.empty((3, B, 1, sc * H, sc * W), f32, dev)
         ops.filter1x(up, m1, out, self.output_upsample)
         return out[0], out[1], out[2]

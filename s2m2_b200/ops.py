@@ -58,7 +58,7 @@ EXPORTS = [
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
-    "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_last_error",
+    "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_filter1x_crop", "s2m2b200_image_pad", "s2m2b200_last_error",
     "s2m2b200_preprocess_u8", "s2m2b200_stem_u8", "s2m2b200_confidence_score", "s2m2b200_disparity_to_points",
     "s2m2b200_version", "s2m2b200_launch_count",
 ]
@@ -97,6 +97,7 @@ class CudaOps:
         self.row_corr_fused = os.environ.get("S2M2_ROWCORR_TC", "1") != "0"   # tcgen05 split-fp16 cost volume with fused LayerNorm
         self.mlp2_fused = os.environ.get("S2M2_MLP2_FUSED", "1") != "0"   # fused 1x1 -> ReLU -> 1x1 (+res) of ConvBlock2D
         self.mlp2_min_tokens = int(os.environ.get("S2M2_MLP2_MIN_TOKENS", "16384"))
+        self.mlp2_max_tokens = int(os.environ.get("S2M2_MLP2_MAX_TOKENS", "120000"))
         self.ln_linear_fused = os.environ.get("S2M2_LNL_FUSED", "1") != "0"  # fused LN + QKV projection tcgen05 kernel
         self.ln_linear_min_tokens = int(os.environ.get("S2M2_LNL_MIN_TOKENS", "16384"))
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
@@ -178,7 +179,8 @@ class CudaOps:
         False if the fused kernel does not take this shape / dtype (the caller then runs the two conv2d launches)."""
         if not self.mlp2_fused or l0.b is None or l2.b is None or l0.cin != l0.cout or l2.cin != l2.cout or l0.kh != 1 or l2.kh != 1:
             return False
-        if x.shape[0] * x.shape[1] * x.shape[2] < self.mlp2_min_tokens:
+        ntok = x.shape[0] * x.shape[1] * x.shape[2]
+        if ntok < self.mlp2_min_tokens or ntok > self.mlp2_max_tokens:     # large maps: two HBM-bound GEMMs are as fast (measured)
             return False
         rc = self.lib.s2m2b200_mlp2(C.byref(tview(x)), C.byref(tview(res)) if res is not None else None, C.byref(tview(out)),
                                     C.c_void_p(l0.w.data_ptr()), C.c_void_p(l0.b.data_ptr()), C.c_void_p(l2.w.data_ptr()),
@@ -383,6 +385,23 @@ class CudaOps:
         p = lambda t: C.c_void_p(t.data_ptr())
         self._chk(self.lib.s2m2b200_filter1x(p(up), p(logits), logits.shape[3], B, H, W, p(out), int(upsample2), self._stream()),
                   "filter1x")
+
+    def filter1x_crop(self, up, logits, out, crop_hw):
+        """filter1x writing only the centre (crop_h, crop_w) window: image_crop (image_utils.py:66-96) fused into the last kernel."""
+        B, H, W, _ = up.shape
+        if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.shape[3] < 9:
+            raise ValueError("filter1x_crop: logits must be contiguous fp32 (B,H,W,>=9)")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_filter1x_crop(p(up), p(logits), logits.shape[3], B, H, W, int(crop_hw[0]), int(crop_hw[1]), p(out),
+                                                  self._stream()), "filter1x_crop")
+
+    # -- pre-processing (SURVEY §8(f) row 1)
+    def image_pad(self, img, factor, out):
+        """image_pad (image_utils.py:27-63) of a contiguous (B,3,H,W) uint8 / fp32 CUDA image into out (B,3,Hn,Wn) fp32."""
+        B, _, H, W = img.shape
+        work = torch.empty((B * 3 * (H // factor) * (W // factor),), dtype=torch.float32, device=img.device)
+        self._chk(self.lib.s2m2b200_image_pad(C.c_void_p(img.data_ptr()), 1 if img.dtype == torch.uint8 else 0, B, H, W, int(factor),
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(work.data_ptr()), self._stream()), "image_pad")
 
     # -- consumers of the output maps (SURVEY §8(f) rows 2, 3)
     def confidence_score(self, conf, crop_hw, margin, out):

@@ -32,6 +32,7 @@ def load_flat_weights(model, flat: torch.Tensor) -> None:
     if off != flat.numel():
         raise ValueError(f"flat weight blob has {flat.numel()} elements, model needs {off}")
     model._packed = None      # repack (fp16 K-major, fused QKV...) on next forward
+    model._graphs = {}        # captured forwards reference the old packed tensors
 
 
 def broadcast_weights(model, src: int = 0) -> int:

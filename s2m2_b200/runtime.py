@@ -31,6 +31,8 @@ class PipelinedRunner:
         self.left = torch.zeros(self.shape, dtype=input_dtype, device=dev)
         self.right = torch.zeros(self.shape, dtype=input_dtype, device=dev)
         self.graph = None
+        if hasattr(model, "auto_graph"):
+            model.auto_graph = False      # this runner owns the captured graph (the module's own same-shape replay would hold a second pool)
         with torch.inference_mode():
             for _ in range(2):                        # packs the weights, builds tables, sets kernel attributes
                 out = model(self.left, self.right)
@@ -77,11 +79,18 @@ class PipelinedRunner:
             self._e_h2d[b].record(cs)
 
     def run(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], host_out: Optional[Sequence[Sequence[torch.Tensor]]] = None):
-        """Enqueue the whole sequence (host→device, forward, device→host for every batch) and return without synchronising.
-        ``host_out[i]``: three pinned host tensors for batch i; default = the runner's two rotating pinned sets."""
+        """Enqueue the whole sequence (host→device, forward, device→host for every batch) and return WITHOUT synchronising: the
+        outputs are valid once ``copy_stream`` has drained (``runner.copy_stream.synchronize()`` or a stream wait).
+        ``host_out[i]``: three pinned host tensors for batch i; the default (the runner's two rotating pinned sets) is only
+        allowed for at most two batches."""
         n = len(batches)
         if n == 0:
             return
+        if host_out is None and n > 2:
+            raise ValueError("run(): with the default host_out only the last two batches would survive (two rotating pinned sets); pass "
+                             "one pinned output triple per batch, or use stream() / infer()")
+        if host_out is not None and len(host_out) != n:
+            raise ValueError(f"run(): {n} batches but {len(host_out)} output triples")
         for l, r in batches:
             self._check(l), self._check(r)
         comp = torch.cuda.current_stream(self.device)

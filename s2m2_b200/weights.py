@@ -4,7 +4,7 @@ The names/shapes reproduce the reference's state-dict contract (SURVEY.md §5
 "checkpoint / resume": e.g. ``transformer.uformer_list.0.enc_attn0.cross_attn.attn.q.weight (C,C)``,
 ``refiner.gru.convz1.weight (C,2C,3,1)``, ``upsample_mask_1x.conv_disp.0.weight (1,16,3,3)``) so a
 reference checkpoint ``CH{C}NTR{N}.pth`` loads unchanged (reference: s2m2.py:14-78,
-model_utils.py:12-43).  ``tests/test_param_spec.py`` checks the list against the real reference
+model_utils.py:12-43).  ``tests/test_oracle.py`` checks the list against the real reference
 module when /root/reference is present.
 
 ``random_state_dict`` generates deterministic synthetic weights with PyTorch's default-init

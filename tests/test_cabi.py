@@ -48,3 +48,37 @@ def test_no_cpu_fallback():
     m = S2M2(32, 1, 1, True)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))
+
+
+def test_module_surface_matches_nn_module_conventions():
+    """state_dict(prefix=..., destination=...) and load_state_dict's _IncompatibleKeys, as wrappers (EMA, DDP-style utilities,
+    submodule-aware loaders) expect them."""
+    from collections import OrderedDict
+
+    import torch
+
+    from s2m2_b200.model import S2M2
+    from s2m2_b200.weights import random_state_dict
+    m = S2M2(32, 1, 1)
+    sd = random_state_dict(32, 1, 0)
+    res = m.load_state_dict(sd)
+    assert res.missing_keys == [] and res.unexpected_keys == []
+    part = dict(sd)
+    dropped = part.pop("ctx_feat.0.weight")
+    part["not.a.key"] = torch.zeros(1)
+    res = m.load_state_dict(part, strict=False)
+    assert res.missing_keys == ["ctx_feat.0.weight"] and res.unexpected_keys == ["not.a.key"]
+    out = m.state_dict(prefix="model.", destination=OrderedDict(extra=1))
+    assert out["extra"] == 1 and torch.equal(out["model.ctx_feat.0.weight"], dropped)
+    assert not out["model.ctx_feat.0.weight"].requires_grad
+    assert isinstance(m.state_dict(keep_vars=True)["ctx_feat.0.weight"], torch.nn.Parameter)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+
+
+def test_runner_rejects_silently_lossy_default():
+    """PipelinedRunner.run() must not accept more batches than its two rotating default output sets."""
+    import inspect
+
+    from s2m2_b200 import runtime
+    src = inspect.getsource(runtime.PipelinedRunner.run)
+    assert "host_out is None and n > 2" in src

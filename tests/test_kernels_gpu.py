@@ -432,7 +432,7 @@ def test_fused_mlp2_convblock_branch(ops, C, M, alias):
     ref = th.mlp2_reference(x, res, l0, l2, ACT_RELU)
     guard = resb[..., C:].clone()
     out = res if alias else torch.full((1, 1, M, C), 9.0, dtype=torch.float16, device=DEV)
-    cu.mlp2_min_tokens = 0
+    cu.mlp2_min_tokens, cu.mlp2_max_tokens = 0, 1 << 30
     assert cu.mlp2(x, res, out, l0, l2, ACT_RELU), "fused mlp2 kernel refused a supported shape"
     torch.cuda.synchronize()
     _close(out, ref, 8e-3, 8e-3, f"mlp2 C={C} M={M}")
@@ -532,3 +532,45 @@ def test_post_confidence_score_and_points():
     rx, rv = PO.disparity_to_points(disp, conf=cf, occ=occ, **kw)
     assert torch.equal(valid.cpu(), rv)
     assert torch.allclose(xyz.cpu(), rx, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("H,W,dtype", [(100, 75, torch.uint8), (64, 96, torch.float32), (70, 96, torch.uint8), (481, 641, torch.uint8)])
+def test_image_pad_kernels(ops, H, W, dtype):
+    """image_pad (image_utils.py:27-63) on the device vs its CPU restatement (which tests/test_post_cpu.py holds to the reference):
+    the original pixels bit-identical, the blurred fill within fp32 summation-order noise."""
+    from oracle import post_oracle as PO
+    from s2m2_b200.pre import image_pad
+    g = torch.Generator().manual_seed(H + W)
+    img = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8).to(dtype)
+    got = image_pad(img.to(DEV)).cpu()
+    ref = PO.image_pad(img)
+    assert got.shape == ref.shape
+    hs, ws = (ref.shape[2] - H) // 2, (ref.shape[3] - W) // 2
+    assert torch.equal(got[:, :, hs:hs + H, ws:ws + W], img.float())
+    _close(got, ref, 1e-5, 2e-3, f"image_pad {H}x{W}")
+
+
+def test_fused_crop_and_device_side_run_stereo_matching():
+    """S2M2.forward(crop_hw=...) == image_crop of the full forward (bit-identical), and pre.stereo_match == the chain
+    image_pad -> forward -> image_crop -> interior confidence mean of run_stereo_matching (model_utils.py:50-95)."""
+    from oracle import post_oracle as PO
+    from s2m2_b200.model import S2M2
+    from s2m2_b200.pre import image_pad, stereo_match
+    from s2m2_b200.weights import random_state_dict
+    m = S2M2(32, 1, 1, use_positivity=True, refine_iter=2, precision="fp16").eval()
+    m.my_load_state_dict(random_state_dict(32, 1, 0))
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    H, W = 70, 100
+    left = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    right = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    lp, rp = image_pad(left), image_pad(right)
+    full = m(lp, rp)
+    crop = m(lp, rp, crop_hw=(H, W))
+    for f, c in zip(full, crop):
+        assert c.shape == (2, 1, H, W)
+        assert torch.equal(PO.image_crop(f, (H, W)), c)
+    d, o, c, score = stereo_match(m, left, right, margin=10)
+    assert torch.equal(d, crop[0][:, 0]) and torch.equal(c, crop[2][:, 0])
+    want = PO.confidence_score(full[2].cpu(), (H, W), 10)
+    assert torch.allclose(score.cpu(), want, rtol=1e-5, atol=1e-6)

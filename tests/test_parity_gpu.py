@@ -346,3 +346,24 @@ def test_pipelined_runner_matches_direct_forward(in_dtype):
         assert torch.equal(a, b)
     with pytest.raises(ValueError):
         runner.infer(batches[0][0][:1], batches[0][1][:1])
+
+
+def test_module_auto_graph_replay_is_bit_identical_to_eager():
+    """S2M2.forward replays a CUDA graph captured on the second call of a (shape, dtype, crop) — the path run_stereo_matching's
+    repeated calls take.  Every call must return exactly what the eager launches return, also after a shape change in between."""
+    C, NTR = 32, 1
+    sd = random_state_dict(C, NTR, 0)
+    m = _model(C, NTR, sd, precision="fp16")
+    e = _model(C, NTR, sd, precision="fp16")
+    e.auto_graph = False
+    pairs = [synthetic_pair(2, 64, 96, 40 + k) for k in range(4)] + [synthetic_pair(1, 96, 64, 50)] + [synthetic_pair(2, 64, 96, 60)]
+    for k, (l, r) in enumerate(pairs):
+        a = m(l.to(DEV), r.to(DEV))
+        b = e(l.to(DEV), r.to(DEV))
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), f"call {k}"
+    assert sum("graph" in v for v in m._graphs.values()) >= 1      # the 64x96 batch-2 shape was captured and replayed
+    u8 = [(l.to(torch.uint8), r.to(torch.uint8)) for l, r in pairs[:3]]
+    for l, r in u8:
+        for x, y in zip(m(l.to(DEV), r.to(DEV), crop_hw=(50, 80)), e(l.to(DEV), r.to(DEV), crop_hw=(50, 80))):
+            assert x.shape[-2:] == (50, 80) and torch.equal(x, y)

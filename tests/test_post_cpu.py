@@ -55,3 +55,22 @@ def test_points_oracle_basic_geometry():
     z = 200.0 * 100.0 / 10.0 / 1000.0
     assert torch.allclose(xyz[0, 1, 1], torch.tensor([(1 - 3.0) * z / 100.0, (1 - 2.0) * z / 100.0, z]))
     assert not bool(valid[0, 0, 0]) and bool(valid[0, 1, 1]) and float(xyz[0, 0, 0, 2]) == 0.0
+
+
+@pytest.mark.parametrize("H,W", [(100, 75), (64, 96), (70, 96), (64, 100)])
+def test_oracle_image_pad_matches_reference(H, W):
+    """post_oracle.image_pad (the checker of the fused GPU pad kernels) against the reference's own image_pad."""
+    import os
+    import sys
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present (GPU box)")
+    sys.path.insert(0, "/root/reference/src")
+    from s2m2.core.utils.image_utils import image_pad as ref_pad
+    import torch
+    from oracle import post_oracle as PO
+    g = torch.Generator().manual_seed(H * W)
+    img = torch.randint(0, 256, (2, 3, H, W), generator=g, dtype=torch.uint8)
+    a = PO.image_pad(img)
+    b = ref_pad(img, 32)
+    assert a.shape == b.shape
+    assert torch.equal(a, b.float())

@@ -44,6 +44,7 @@ def main():
             ops.conv2d(h, l2, ACT_NONE, z, res=z)
 
         ops.ffn_min_tokens = ops.ffn_min_tokens_wide = ops.mlp2_min_tokens = 0
+        ops.mlp2_max_tokens = 1 << 30
         t_f = timeit(lambda: ops.ffn(z, l0, l2))
         t_u = timeit(unfused)
         gf = 4.0 * M * C * C / 1e9

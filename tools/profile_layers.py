@@ -68,6 +68,7 @@ def main():
     m.my_load_state_dict(random_state_dict(C, NTR, 0))
     m = m.cuda()
     m.ops = TimedOps()
+    m.auto_graph = False      # per-op CUDA events need eager launches
     left, right = synthetic_pair(a.batch, a.height, a.width, 1)
     left, right = left.cuda(), right.cuda()
     with torch.no_grad():
