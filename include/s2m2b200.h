@@ -66,6 +66,18 @@ typedef struct {
   int32_t batch;                /* >= 1 */
   int64_t x_bs, w_bs, y_bs;
   int32_t impl;                 /* 0 = auto, 1 = force CUDA-core fp32 FMA kernel, 2 = force tcgen05 kernel */
+  /* Epilogue modes of the tcgen05 path (fp16 in / out), a = act(acc + bias), R1 = res, R2 = res2 at the same pixel:
+   *   0  y = a (+ R1)                                   the plain layer with its residual
+   *   1  y[:, n] = a * R1[:, n - res_from]  for n >= res_from (columns below res_from: y = a)
+   *         ConvGRU: [z | r] = sigmoid(conv([h, x])) with r * h formed in place of r (refinenet.py:25-27,31-33)
+   *   2  g = clamp(a, .01, .99);  y = g * R1 + (1 - g) * R2
+   *         FeatureFusion's gate applied to its two inputs (feature_fusion.py:27-29); the fusion branch then adds this as its residual
+   *   3  y = R1 * a + (1 - R1) * R2
+   *         ConvGRU state update h = (1 - z) h + z q, q = tanh(conv([r h, x])), R1 = z, R2 = h, y may alias R2 (refinenet.py:28-29,34-35)
+   * res_from: first output column that has an R1 column (mode 1), 0 otherwise.  Modes 1-3 exist on the tcgen05 path only:
+   * s2m2b200_conv2d returns 1 (nothing launched) when the layer does not qualify, and the caller composes the step from separate ops. */
+  S2m2Tensor res2;              /* R2 of modes 2 / 3 (fp16 view); ptr NULL otherwise */
+  int32_t emode, res_from;
 } S2m2Conv;
 int s2m2b200_conv2d(const S2m2Conv* a, void* stream);
 

@@ -56,9 +56,16 @@ int s2m2b200_conv2d(const S2m2Conv* a, void* stream) {
   } else {
     S2M2_CHECK(y.C == a->Cout && y.H == Ho && y.W == Wo && y.N == x.N, "conv2d: y shape (%d,%d,%d,%d) != expected (%d,%d,%d,%d)",
                y.N, y.H, y.W, y.C, x.N, Ho, Wo, a->Cout);
-    if (a->res.ptr) S2M2_CHECK(a->res.C == y.C && npix(a->res) == npix(y), "conv2d: residual shape mismatch");
+    if (a->res.ptr) S2M2_CHECK(a->res.C == y.C - (a->emode == 1 ? a->res_from : 0) && npix(a->res) == npix(y), "conv2d: residual shape mismatch");
+    if (a->res2.ptr) S2M2_CHECK(a->res2.C == y.C && npix(a->res2) == npix(y) && a->res2.dtype == S2M2_F16, "conv2d: res2 shape / dtype mismatch");
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (a->emode != 0) {          // fused gate / GRU epilogues: tcgen05 path only (the caller composes them from separate ops otherwise)
+    S2M2_CHECK(a->emode >= 1 && a->emode <= 3 && a->res.ptr && !a->shuffle2x2, "conv2d: bad epilogue mode %d", a->emode);
+    S2M2_CHECK(a->emode == 1 || a->res2.ptr, "conv2d: epilogue mode %d needs res2", a->emode);
+    if (a->impl == 1 || !conv_tc_supported(a)) return 1;   // not applicable: the caller composes the step from separate ops
+    return conv_tc_launch(a, s);
+  }
   if (a->impl == 2) {
     S2M2_CHECK(conv_tc_supported(a), "conv2d: tcgen05 kernel forced but shape/dtype unsupported");
     return conv_tc_launch(a, s);

@@ -38,6 +38,9 @@ struct TcP {
   int tma_res;           // (with tma_store) the residual tile is TMA-loaded into the staging buffer instead of scattered global loads
   int tma_store;         // epilogue stages the tile in shared memory and writes it with cp.async.bulk.tensor (fp16, no scatter)
   int dbg;               // S2M2_TC_DBG experiments: 1 = no global stores, 2 = epilogue only drains (no math / stores)
+  const void* res2;      // epilogue modes 2 / 3: second tile operand (fp16), read with plain loads
+  long long res2_ld;
+  int emode, res_from;   // include/s2m2b200.h: 0 add, 1 multiply (columns >= res_from), 2 gate blend, 3 GRU update
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       constexpr int NCH = CG / 16;                       // 16-column chunks per warp
       uint4 rpre[NCH][2];
       const bool has_res = p.res != nullptr && !p.shuffle;
-      if (has_res && p.rh && !p.tma_res) {
+      if (has_res && p.rh && !p.tma_res && p.emode == 0) {
         // full-sector reads, same lane-pair trick as the stores: instruction 1 reads the even row of the pair (low half by
         // the even lane, high half by the odd lane), instruction 2 the odd row; one exchange puts the halves back in place.
         const bool odd = lane & 1;
@@ -536,13 +539,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       if (p.tma_store) {   // the previous tile's bulk store must have read the staging tile before it is overwritten
         if (lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (p.tma_res && tile_ok && n0 + half * CG < p.Cout) {   // residual tile (same box as the store) -> staging buffer
+          if (p.tma_res && tile_ok && n0 + half * CG < p.Cout && n0 + half * CG >= p.res_from) {   // residual tile (same box as the store) -> staging buffer
             const int r0 = q * 32;
             int cx, cy;
             if (p.flat) { cx = x0 + r0; cy = 0; }
             else { cx = x0 + r0 % p.tw; cy = y0 + r0 / p.tw; }
             mbar_expect_tx(rbar0 + 8 * (warp - 2), 32 * CG * 2);
-            tma_load_4d(&maps.res, stg_u32, rbar0 + 8 * (warp - 2), n0 + half * CG, cx, cy, img);
+            tma_load_4d(&maps.res, stg_u32, rbar0 + 8 * (warp - 2), n0 + half * CG - p.res_from, cx, cy, img);
           }
         }
         __syncwarp();
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       mbar_wait(tfull0 + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      const bool use_tma_res = p.tma_res && tile_ok;
+      const bool use_tma_res = p.tma_res && tile_ok && n0 + half * CG >= p.res_from;
       if (use_tma_res && n0 + half * CG < p.Cout) {
         mbar_wait(rbar0 + 8 * (warp - 2), rt & 1);
         ++rt;
@@ -610,18 +613,37 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         } else {
           off = opix * p.y_ld + n;
           if (use_tma_res) {
+            // emode 0: + R1;  1: * R1;  2: gate blend g R1 + (1 - g) R2;  3: GRU update R1 q + (1 - R1) R2   (s2m2b200.h)
+            uint4 r2v[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (p.emode >= 2 && valid) {
+              const uint4* r2p = (const uint4*)((const __half*)p.res2 + opix * p.res2_ld + n);
+              r2v[0] = r2p[0]; r2v[1] = r2p[1];                       // plain loads: y may alias R2 (in-place state update)
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const uint32_t lin = (uint32_t)lane * (CG * 2) + (uint32_t)(c * 2 + u) * 16;
               const uint4 rv = *(const uint4*)(stg + (lin ^ (((lin >> 7) & SWZ_MASK) << 4)));
               const __half2* hr = (const __half2*)&rv;
+              const __half2* h2 = (const __half2*)&r2v[u];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(hr[i]);
-                v[8 * u + 2 * i] += f.x; v[8 * u + 2 * i + 1] += f.y;
+                float& a0 = v[8 * u + 2 * i];
+                float& a1 = v[8 * u + 2 * i + 1];
+                if (p.emode == 0) { a0 += f.x; a1 += f.y; }
+                else if (p.emode == 1) { a0 *= f.x; a1 *= f.y; }
+                else {
+                  const float2 g = __half22float2(h2[i]);
+                  if (p.emode == 2) {
+                    const float w0 = fminf(fmaxf(a0, 0.01f), 0.99f), w1 = fminf(fmaxf(a1, 0.01f), 0.99f);
+                    a0 = w0 * f.x + (1.0f - w0) * g.x; a1 = w1 * f.y + (1.0f - w1) * g.y;
+                  } else {
+                    a0 = f.x * a0 + (1.0f - f.x) * g.x; a1 = f.y * a1 + (1.0f - f.y) * g.y;
+                  }
+                }
               }
             }
-          } else if (has_res && valid) {
+          } else if (has_res && valid && p.emode == 0) {
             if (p.rh) {
               const __half2* hr = (const __half2*)&rpre[c][0];
 #pragma unroll
@@ -761,6 +783,13 @@ int conv_tc_supported(const S2m2Conv* a) {
     if (res.ld % 8 || !aligned(res.ptr, 16)) return 0;
   }
   if ((long long)x.N * x.H * x.W < 256) return 0;   // tiny problems: launch-bound either way
+  if (a->emode != 0) {   // fused gate / GRU epilogues ride the TMA-store + TMA-residual path of the persistent kernel
+    if (y.dtype != S2M2_F16 || a->shuffle2x2 || !res.ptr || res.dtype != S2M2_F16 || a->stride != 1) return 0;
+    if (a->emode == 1 && (a->res_from % 64 || a->res_from < 0 || a->res_from >= a->Cout)) return 0;
+    if (a->emode != 1 && a->res_from != 0) return 0;
+    if (a->emode >= 2 && (!a->res2.ptr || a->res2.dtype != S2M2_F16 || a->res2.ld % 8 || !aligned(a->res2.ptr, 16))) return 0;
+    if (getenv("S2M2_TC_V1") || getenv("S2M2_TC_NO_TMA_STORE") || getenv("S2M2_TC_NO_TMA_RES")) return 0;
+  }
   return tc_device_ok() ? 1 : 0;
 }
 
@@ -857,6 +886,8 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   p.Cout = a->Cout; p.KW = a->KW; p.ph = a->pad_h; p.pw = a->pad_w; p.taps = a->KH * a->KW; p.stride = a->stride;
   p.cpb1 = x.C / TC_BK; p.cpb2 = x2.ptr ? x2.C / TC_BK : 0;
   p.act = a->act; p.shuffle = a->shuffle2x2; p.Cr = a->shuffle2x2 ? a->Cout / 4 : a->Cout;
+  p.emode = a->emode; p.res_from = a->emode == 1 ? a->res_from : 0;
+  p.res2 = a->res2.ptr; p.res2_ld = a->res2.ptr ? a->res2.ld : 0;
   long long mtiles;
   if (p.flat && !a->shuffle2x2) {
     p.Ho = 1; p.Wo = (int)((long long)x.N * x.H * x.W); p.tw = TC_BM; p.th = 1; p.tiles_x = cdiv(p.Wo, TC_BM); p.tiles_y = 1;
@@ -938,7 +969,8 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
         cuuint64_t rstr[3];
         if (p.flat) { rstr[0] = (cuuint64_t)res.ld * 2; rstr[1] = rstr[0] * dims[1]; rstr[2] = rstr[1]; }
         else { rstr[0] = (cuuint64_t)res.ld * 2; rstr[1] = rstr[0] * y.W; rstr[2] = rstr[1] * y.H; }
-        CUresult r2 = get_encode()(&maps.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(res.ptr), dims, rstr, box, estr,
+        cuuint64_t rdims[4] = {(cuuint64_t)res.C, dims[1], dims[2], dims[3]};   // (mode 1: the residual has Cout - res_from channels)
+        CUresult r2 = get_encode()(&maps.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(res.ptr), rdims, rstr, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         S2M2_CHECK(r2 == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(residual) failed: %d", (int)r2);
       } else {

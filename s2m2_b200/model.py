@@ -426,6 +426,11 @@ class S2M2(nn.Module):
         """FeatureFusion (feature_fusion.py:24-33); conv over cat([z0,z1]) reads both sources directly."""
         d = p["dim"]
         t = self._c(z0, p["gf0"], ACT_GELU, x2=z1)                   # (.., 3d): gate hidden | fusion hidden
+        if self.ops.conv_emodes(t):
+            # the gate's conv epilogue forms  clamp(sigmoid(.)) z0 + (1 - clamp) z1  (mode 2); the fusion conv adds it as its residual
+            bl = self._new(z0, d)
+            if self.ops.conv2d(t[..., :d], p["g2"], ACT_SIGMOID, bl, res=z0, res2=z1, emode=self.ops.EMODE_BLEND):
+                return self._c(t[..., d:], p["f2"], res=bl)
         g = self._c(t[..., :d], p["g2"], ACT_SIGMOID)
         f = self._c(t[..., d:], p["f2"])
         self.ops.gate_blend(f, g, z0, z1, f)
@@ -635,6 +640,15 @@ class S2M2(nn.Module):
             self._unet(x, lr["unet"], out0=xin)          # the U-Net's last ConvBlock writes straight into the GRU input slot [h | x]
             del x
             for zr, q in ((lr["zr1"], lr["q1"]), (lr["zr2"], lr["q2"])):     # ConvGRU (refinenet.py:22-36)
+                if ops.conv_emodes(hx):
+                    # [z | r*h] = sigmoid(conv([h, x])) with r * h formed in the epilogue (mode 1 on the r columns), then
+                    # h = (1 - z) h + z tanh(conv([r*h, x])) as the q conv's epilogue (mode 3), written over h in place
+                    zrt = self._new(hx, 2 * C)
+                    if ops.conv2d(hx, zr, ACT_SIGMOID, zrt, res=hidden, emode=ops.EMODE_MUL, res_from=C):
+                        if not ops.conv2d(zrt[..., C:], q, ACT_TANH, hidden, res=zrt[..., :C], x2=xin, res2=hidden, emode=ops.EMODE_GRU):
+                            qt = self._c(zrt[..., C:], q, ACT_TANH, x2=xin)
+                            ops.gru_update(zrt[..., :C], qt, hidden)
+                        continue
                 zrt = self._c(hx, zr, ACT_SIGMOID)
                 ops.mul(zrt[..., C:], hidden, rh)
                 qt = self._c(rh, q, ACT_TANH, x2=xin)                       # conv over cat([r*h, x]) reads the two sources in place

@@ -28,7 +28,8 @@ class S2m2Conv(C.Structure):
                 ("w", C.c_void_p), ("w_dtype", C.c_int32), ("bias", C.c_void_p),
                 ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
                 ("Cout", C.c_int32), ("act", C.c_int32), ("shuffle2x2", C.c_int32), ("batch", C.c_int32),
-                ("x_bs", C.c_int64), ("w_bs", C.c_int64), ("y_bs", C.c_int64), ("impl", C.c_int32)]
+                ("x_bs", C.c_int64), ("w_bs", C.c_int64), ("y_bs", C.c_int64), ("impl", C.c_int32),
+                ("res2", S2m2Tensor), ("emode", C.c_int32), ("res_from", C.c_int32)]
 
 
 _lib = None
@@ -95,6 +96,7 @@ class CudaOps:
         # C > 256 runs the one-tile-at-a-time kernel (the tile pair does not fit TMEM): it needs >= 2 tiles per SM to win
         self.ffn_min_tokens_wide = int(os.environ.get("S2M2_FFN_MIN_TOKENS_WIDE", "37888"))
         self.row_corr_fused = os.environ.get("S2M2_ROWCORR_TC", "1") != "0"   # tcgen05 split-fp16 cost volume with fused LayerNorm
+        self.fuse_epilogues = os.environ.get("S2M2_FUSE_EPILOGUES", "1") != "0"   # gate blend / GRU steps as conv epilogue modes
         self.mlp2_fused = os.environ.get("S2M2_MLP2_FUSED", "1") != "0"   # fused 1x1 -> ReLU -> 1x1 (+res) of ConvBlock2D
         self.mlp2_min_tokens = int(os.environ.get("S2M2_MLP2_MIN_TOKENS", "16384"))
         self.mlp2_max_tokens = int(os.environ.get("S2M2_MLP2_MAX_TOKENS", "120000"))
@@ -140,8 +142,17 @@ class CudaOps:
         return self._pe[key]
 
     # -- GEMM-class
-    def conv2d(self, x, cw, act, out, res=None, x2=None, batch=1, x_bs=0, w_bs=0, y_bs=0):
+    # epilogue modes of the tcgen05 conv (include/s2m2b200.h): the gate / GRU element-wise steps folded into the producing layer
+    EMODE_ADD, EMODE_MUL, EMODE_BLEND, EMODE_GRU = 0, 1, 2, 3
+
+    def conv_emodes(self, x) -> bool:
+        """Are the fused gate / GRU epilogues available for activations like ``x``?  (fp16 tcgen05 path only.)"""
+        return self.fuse_epilogues and x.dtype == torch.float16 and self.conv_impl != 1
+
+    def conv2d(self, x, cw, act, out, res=None, x2=None, batch=1, x_bs=0, w_bs=0, y_bs=0, res2=None, emode=0, res_from=0):
         a = S2m2Conv()
+        a.res2 = tview(res2) if res2 is not None else _NULL_T
+        a.emode, a.res_from = emode, res_from
         a.x = tview(x)
         a.x2 = tview(x2) if x2 is not None else _NULL_T
         a.y = tview(out)
@@ -156,7 +167,11 @@ class CudaOps:
         a.Cout, a.act, a.shuffle2x2 = cw.cout, act, 1 if cw.shuffle else 0
         a.batch, a.x_bs, a.w_bs, a.y_bs = batch, x_bs, w_bs, y_bs
         a.impl = self.conv_impl
-        self._chk(self.lib.s2m2b200_conv2d(C.byref(a), self._stream()), f"conv2d[{cw.name}]")
+        rc = self.lib.s2m2b200_conv2d(C.byref(a), self._stream())
+        if rc == 1 and emode != 0:
+            return False                 # fused epilogue mode not available for this layer: the caller runs the separate ops
+        self._chk(rc, f"conv2d[{cw.name}]")
+        return True
 
     def ffn(self, z, l0, l2):
         """Fused LN -> Linear -> GELU -> Linear -> +z in place; False if the fused kernel does not take this shape/dtype."""
@@ -213,6 +228,8 @@ class CudaOps:
         a.x = S2m2Tensor(f.data_ptr(), F32, 1, 1, w, Cc, Cc)
         a.x2 = _NULL_T
         a.res = _NULL_T
+        a.res2 = _NULL_T
+        a.emode = a.res_from = 0
         a.y = S2m2Tensor(cv.data_ptr(), F32, 1, 1, w, w, w)
         a.w = f[B:].data_ptr()
         a.w_dtype = F32

@@ -574,3 +574,28 @@ def test_fused_crop_and_device_side_run_stereo_matching():
     assert torch.equal(d, crop[0][:, 0]) and torch.equal(c, crop[2][:, 0])
     want = PO.confidence_score(full[2].cpu(), (H, W), 10)
     assert torch.allclose(score.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("emode,kh,kw,cin,cout,act", [(1, 3, 1, 128, 128, ACT_SIGMOID), (1, 1, 3, 256, 512, ACT_SIGMOID), (2, 1, 1, 256, 256, ACT_SIGMOID),
+                                                     (2, 1, 1, 64, 64, ACT_SIGMOID), (3, 3, 1, 128, 64, ACT_TANH), (3, 1, 3, 512, 256, ACT_TANH)])
+def test_conv_epilogue_modes(ops, emode, kh, kw, cin, cout, act):
+    """The gate-blend / GRU epilogue modes of the tcgen05 conv (include/s2m2b200.h) vs the composition of separate torch ops;
+    strided views, the GRU update written in place over R2."""
+    cu, th = ops
+    g = torch.Generator().manual_seed(emode * 100 + cin + cout)
+    N, H, W = 2, 37, 53
+    x = _rand((N, H, W, cin), torch.float16, g)
+    w = _rand((cout, kh * kw * cin), torch.float16, g, 1.0 / math.sqrt(kh * kw * cin))
+    cw = ConvW(w, _rand((cout,), torch.float32, g, 0.3), kh, kw, 1, kh // 2, kw // 2, cin, cout, False, f"emode{emode}")
+    res_from = cout // 2 if emode == 1 else 0
+    r1 = torch.rand((N, H, W, cout - res_from + 8), generator=g).to(DEV).half()[..., :cout - res_from]
+    r2b = _rand((N, H, W, 2 * cout), torch.float16, g)
+    r2 = r2b[..., :cout] if emode >= 2 else None
+    ref = torch.empty((N, H, W, cout), dtype=torch.float16, device=DEV)
+    th.conv2d(x, cw, act, ref, res=r1, res2=r2, emode=emode, res_from=res_from)
+    out = r2 if emode == 3 else torch.full((N, H, W, cout), 9.0, dtype=torch.float16, device=DEV)    # mode 3: in place over R2
+    guard = r2b[..., cout:].clone()
+    cu.conv2d(x, cw, act, out, res=r1, res2=r2, emode=emode, res_from=res_from)
+    torch.cuda.synchronize()
+    _close(out, ref, 6e-3, 6e-3, f"conv epilogue mode {emode} {kh}x{kw} {cin}->{cout}")
+    assert torch.equal(r2b[..., cout:], guard)

@@ -47,7 +47,13 @@ class TorchOps:
         return self._pe[key]
 
     # GEMM-class
-    def conv2d(self, x, cw, act, out, res=None, x2=None):
+    EMODE_ADD, EMODE_MUL, EMODE_BLEND, EMODE_GRU = 0, 1, 2, 3
+    fuse_epilogues = True            # CPU schedule tests exercise the fused gate / GRU epilogue route of the fp16 schedule
+
+    def conv_emodes(self, x) -> bool:
+        return self.fuse_epilogues and x.dtype == torch.float16
+
+    def conv2d(self, x, cw, act, out, res=None, x2=None, res2=None, emode=0, res_from=0):
         xin = x if x2 is None else torch.cat([x, x2], dim=3)
         assert xin.shape[3] == cw.cin, (cw.name, xin.shape, cw.cin)
         w4 = cw.w.float().reshape(cw.cout, cw.kh, cw.kw, cw.cin).permute(0, 3, 1, 2)
@@ -57,10 +63,22 @@ class TorchOps:
             n, h, w, c4 = y.shape
             c = c4 // 4
             y = y.reshape(n, h, w, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, c)
-        if res is not None:
-            y = y + res.float()
+        if emode == 0:
+            if res is not None:
+                y = y + res.float()
+        elif emode == 1:           # y[..., n] = a * R1[..., n - res_from] for n >= res_from   (include/s2m2b200.h)
+            y = torch.cat([y[..., :res_from], y[..., res_from:] * res.float()], dim=3)
+        elif emode == 2:           # gate blend
+            g = y.clamp(0.01, 0.99)
+            y = g * res.float() + (1 - g) * res2.float()
+        elif emode == 3:           # GRU state update
+            z = res.float()
+            y = z * y + (1 - z) * res2.float()
+        else:
+            raise ValueError(emode)
         assert out.shape == y.shape, (cw.name, out.shape, y.shape)
         out.copy_(y.to(out.dtype))
+        return True
 
     def ffn(self, z, l0, l2):
         """The fused kernel's semantics (used by the GPU kernel test); returning False makes the schedule take the
