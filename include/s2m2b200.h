@@ -237,6 +237,9 @@ const char* s2m2b200_last_error(void);
 const char* s2m2b200_version(void);
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t s2m2b200_launch_count(void);
+/* Plan mode (thread-local; returns the previous value): while on, every op above runs its host-side checks and dispatch and
+ * returns the code it would return, but enqueues nothing — how s2m2b200_workspace_bytes walks the forward schedule. */
+int s2m2b200_set_plan_mode(int on);
 
 #ifdef __cplusplus
 }

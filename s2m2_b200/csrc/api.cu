@@ -5,12 +5,26 @@
 
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace s2m2 {
 
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+thread_local int g_plan = 0;
+
+bool plan_without_device() {
+  if (!g_plan) return false;
+  static int have = -1;
+  if (have < 0) {
+    int n = 0;
+    have = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+    (void)cudaGetLastError();
+  }
+  return have == 0;
+}
 
 bool pdl_enabled() {   // S2M2_PDL=1 turns programmatic dependent launch on.  Default off: inside the captured CUDA graph the
   static int on = -1;  // kernel-to-kernel gaps are already hidden and the measured forward time did not improve (34.1 vs 34.3 ms).
@@ -20,6 +34,13 @@ bool pdl_enabled() {   // S2M2_PDL=1 turns programmatic dependent launch on.  De
   }
   return on != 0;
 }
+
+static CUresult encode_stub(CUtensorMap* m, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  memset(m, 0, sizeof(*m));
+  return CUDA_SUCCESS;
+}
+void* plan_encode_stub() { return (void*)encode_stub; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -39,7 +60,12 @@ using namespace s2m2;
 extern "C" {
 
 const char* s2m2b200_last_error(void) { return g_err; }
-const char* s2m2b200_version(void) { return "s2m2b200 0.1 sm_100a (cuda-core fp32 + tcgen05 f16 implicit GEMM)"; }
+int s2m2b200_set_plan_mode(int on) {   // returns the previous value (thread-local)
+  const int prev = g_plan;
+  g_plan = on ? 1 : 0;
+  return prev;
+}
+const char* s2m2b200_version(void) { return "s2m2b200 0.2 sm_100a (tcgen05 f16 implicit GEMM, fused token kernels, split-fp16 cost volume; cuda-core fp32 parity path)"; }
 int64_t s2m2b200_launch_count(void) { return g_launches; }
 
 int s2m2b200_conv2d(const S2m2Conv* a, void* stream) {

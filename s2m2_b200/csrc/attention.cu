@@ -168,7 +168,7 @@ static int launch_attn(const AttnP& p, cudaStream_t s) {
   static bool attr_set[S2M2_MAX_DEVICES] = {false};
   const int di = current_device_index();
   if (!attr_set[di]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = set_func_attr(attention_simt_kernel<MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     S2M2_CHECK(e == cudaSuccess, "attention_simt: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set[di] = true;
   }

@@ -420,7 +420,7 @@ static int launch_a2(const A2Maps& maps, const A2P& p, cudaStream_t s) {
   static int sms_of[64] = {0};
   if (dev < 0 || dev >= 64) dev = 0;
   if (!sms_of[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention2d_tc_kernel<PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(attention2d_tc_kernel<PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "attention2d_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

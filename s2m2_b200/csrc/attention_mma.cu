@@ -266,7 +266,7 @@ static int launch_fa(const AttnP& p, cudaStream_t s) {
   static bool attr[S2M2_MAX_DEVICES] = {false};
   const int di = current_device_index();
   if (!attr[di]) {
-    cudaFuncSetAttribute(attention_mma_kernel<D, FA_BK, PE, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    set_func_attr(attention_mma_kernel<D, FA_BK, PE, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr[di] = true;
   }
   dim3 grid(cdiv(p.N, FA_BQ), p.heads * VS, p.S);

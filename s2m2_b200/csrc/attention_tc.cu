@@ -15,6 +15,8 @@
 // through one TMA ring that runs ahead across tile boundaries, so the next tile's loads hide behind the current math.
 //   warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..17 = softmax / epilogue.
 // Reference op: F.scaled_dot_product_attention in the 1-D blocks (attentions.py:50,86,91,119-161).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 #include "attention.cuh"
@@ -46,17 +48,22 @@ __device__ __forceinline__ float ex2_approx(float x) {   // x <= 0 here: no rang
   return y;
 }
 
+static int atc_nst_override() {   // d = 256: a three-slot K/V ring where it fits next to Q and P (N <= 192; 430 -> 394 us at
+  static const int v = getenv("S2M2_ATC_NST") ? atoi(getenv("S2M2_ATC_NST")) : 3;   // S=4096, N=176); S2M2_ATC_NST=2 keeps two slots
+  return v;
+}
 static size_t atc_smem_bytes(int D, int NKB) {
-  const int NST = D >= 256 ? 2 : 8;
+  int NST = D >= 256 ? 2 : 8;
+  if (D >= 256 && atc_nst_override() == 3 && NKB <= 3) NST = 3;
   return (size_t)128 * D * 2 + (size_t)NKB * 16384 + (size_t)NST * 64 * D * 2 + (6 + 2 * NST) * 8 + 16 + 2 * ATC_SPLIT * 128 * 4 + 1024;
 }
 
-template <int D>
+template <int D, int NSTX = 0>
 __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __grid_constant__ AtcMaps maps, const AtcP p) {
   constexpr int KC = D / 64;                       // 64-channel chunks of the head dim
   constexpr uint32_t Q_BYTES = 128 * D * 2;        // KC chunks of [128 rows][128 B]
   constexpr uint32_t BLK_BYTES = 64 * D * 2;       // one ring slot: K block or V block, both KC x [64 keys][128 B]
-  constexpr int NST = atc_stages<D>();
+  constexpr int NST = NSTX ? NSTX : atc_stages<D>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -290,7 +297,7 @@ int attention_tc_supported(const AttnP& p) {
 
 size_t attention_tc_workspace_bytes(const AttnP& p) { (void)p; return 16; }   // no scratch needed any more (kept for the ABI)
 
-template <int D>
+template <int D, int NSTX = 0>
 static int launch_atc(const AtcMaps& maps, const AtcP& p, cudaStream_t s) {
   const size_t smem = atc_smem_bytes(D, p.NKB);
   S2M2_CHECK(smem <= 227 * 1024, "attention_tc: shared memory %zu too large", smem);
@@ -299,14 +306,14 @@ static int launch_atc(const AtcMaps& maps, const AtcP& p, cudaStream_t s) {
   const int di = current_device_index();
   int& sms = sms_of[di];
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = set_func_attr(attention_tc_kernel<D, NSTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     S2M2_CHECK(e == cudaSuccess, "attention_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     attr[di] = true;
   }
-  launch_k(attention_tc_kernel<D>, p.tiles < sms ? p.tiles : sms, ATC_THREADS, smem, s, maps, p);
+  launch_k(attention_tc_kernel<D, NSTX>, p.tiles < sms ? p.tiles : sms, ATC_THREADS, smem, s, maps, p);
   S2M2_LAUNCH_OK("attention_tc");
   return 0;
 }
@@ -335,6 +342,7 @@ int attention_tc_launch(const AttnP& a, void* workspace, cudaStream_t s) {
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     S2M2_CHECK(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "attention_tc: cuTensorMapEncodeTiled(qkv) failed: %d %d", (int)r1, (int)r2);
   }
+  if (D == 256 && atc_nst_override() == 3 && p.NKB <= 3) return launch_atc<256, 3>(maps, p, s);
   if (D == 256) return launch_atc<256>(maps, p, s);
   if (D == 128) return launch_atc<128>(maps, p, s);
   return launch_atc<64>(maps, p, s);

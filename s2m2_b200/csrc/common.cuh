@@ -21,8 +21,19 @@ extern long long g_launches;
     }                                         \
   } while (0)
 
+// ---- plan mode ----------------------------------------------------------------------------------
+// With the (thread-local) plan flag set every exported op runs its host-side checks and its dispatch — which kernel takes this
+// shape, which return code the caller gets — but enqueues nothing.  The host-side forward (host_forward.cu) walks its schedule
+// once in this mode to size the workspace (s2m2b200_workspace_bytes).  On a box without a CUDA device the plan assumes the
+// sm_100a target (tests/test_host_forward_cpu.py walks the schedule that way).
+extern thread_local int g_plan;
+static inline bool plan_mode() { return g_plan != 0; }
+bool plan_without_device();
+void* plan_encode_stub();   // stands in for cuTensorMapEncodeTiled in a device-less plan: the maps are never used, only the return codes
+
 #define S2M2_LAUNCH_OK(name)                                                        \
   do {                                                                              \
+    if (s2m2::plan_mode()) break;                                                   \
     cudaError_t e__ = cudaGetLastError();                                           \
     if (e__ != cudaSuccess) {                                                       \
       s2m2::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
@@ -44,6 +55,7 @@ bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  if (plan_mode()) return;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -64,6 +76,13 @@ static inline int current_device_index() {
   int d = 0;
   if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= S2M2_MAX_DEVICES) d = 0;
   return d;
+}
+
+// cudaFuncSetAttribute that a device-less plan (see plan mode above) survives
+template <typename F>
+static inline cudaError_t set_func_attr(F* kernel, cudaFuncAttribute attr, int value) {
+  if (plan_without_device()) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, attr, value);
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

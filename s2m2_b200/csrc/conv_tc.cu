@@ -736,6 +736,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
 
 // ---- host side -----------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  if (plan_without_device()) return (PFN_cuTensorMapEncodeTiled_v12000)plan_encode_stub();
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -750,6 +751,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static bool tc_device_ok() {
+  if (plan_without_device()) return true;
   static int ok_of[S2M2_MAX_DEVICES] = {0};   // 0 = unknown, 1 = yes, 2 = no  (per device)
   const int di = current_device_index();
   if (ok_of[di] == 0) {
@@ -829,7 +831,7 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
   static bool attr[S2M2_MAX_DEVICES] = {false};
   const int di = current_device_index();
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr[di] = true;
   }
@@ -848,7 +850,7 @@ static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles
   const int di = current_device_index();
   int& sms = sms_of[di];
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(conv_tc_persistent_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);

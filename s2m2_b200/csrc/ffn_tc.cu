@@ -603,7 +603,7 @@ static int launch_mlp2(const FfnMaps& maps, const Mlp2P& p, cudaStream_t s) {
   static int sms_of[64] = {0};
   if (dev < 0 || dev >= 64) dev = 0;
   if (!sms_of[dev]) {   // per device: the attribute belongs to the (function, device) pair
-    cudaError_t e = cudaFuncSetAttribute(mlp2_tc_kernel<C, LN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(mlp2_tc_kernel<C, LN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "mlp2_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -633,7 +633,7 @@ static int launch_ffn(const FfnMaps& maps, const FfnP& p, cudaStream_t s) {
   const int di = current_device_index();
   int& sms = sms_of[di];
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(ffn_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "ffn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);

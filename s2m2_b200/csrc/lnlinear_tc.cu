@@ -239,7 +239,7 @@ static int launch_lnl(const LnlMaps& maps, const LnlP& p, cudaStream_t s) {
   const int di = current_device_index();
   int& sms = sms_of[di];
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(lnlinear_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(lnlinear_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "lnlinear_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);

@@ -233,7 +233,7 @@ static int launch_rc(const RcMaps& maps, const RcP& p, cudaStream_t s) {
   static bool attr[S2M2_MAX_DEVICES] = {false};
   const int di = current_device_index();
   if (!attr[di]) {
-    cudaError_t e = cudaFuncSetAttribute(rowcorr_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(rowcorr_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "rowcorr_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr[di] = true;
   }

@@ -394,7 +394,7 @@ int sinkhorn_cluster_launch(const float* cv, int B, int h, int w, float* disp, f
   static bool attr[S2M2_MAX_DEVICES][3] = {{false}};
   const int di = current_device_index();
   if (!attr[di][ki]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    cudaError_t e = set_func_attr(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
     S2M2_CHECK(e == cudaSuccess, "sinkhorn_cluster: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr[di][ki] = true;
   }

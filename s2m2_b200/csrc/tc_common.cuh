@@ -100,6 +100,7 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
 }
 
 inline PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  if (plan_without_device()) return (PFN_cuTensorMapEncodeTiled_v12000)plan_encode_stub();
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -113,6 +114,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 inline bool device_ok() {
+  if (plan_without_device()) return true;
   static int ok_of[S2M2_MAX_DEVICES] = {0};   // 0 = unknown, 1 = yes, 2 = no  (per device)
   const int di = current_device_index();
   if (ok_of[di] == 0) {

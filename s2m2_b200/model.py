@@ -64,6 +64,7 @@ class S2M2(nn.Module):
         import os
         self.auto_graph = os.environ.get("S2M2_AUTO_GRAPH", "1") != "0"   # replay a captured CUDA graph on repeated same-shape calls
         self.auto_graph_slots = int(os.environ.get("S2M2_AUTO_GRAPH_SLOTS", "2"))
+        self.auto_graph_warm = int(os.environ.get("S2M2_AUTO_GRAPH_WARM", "1"))   # eager calls of a shape before its graph is captured
         self._graphs = {}
 
     # ---- nn.Module surface -------------------------------------------------------------------
@@ -494,8 +495,8 @@ class S2M2(nn.Module):
         the last kernel then writes only that centre window, i.e. image_crop (image_utils.py:66-96, the step
         run_stereo_matching applies to each output, model_utils.py:89-91) is fused into it.
 
-        Repeated calls with the same (shape, dtype, crop) replay a CUDA graph captured on the second such call: the ~900 kernel
-        launches of one forward then cost one graph launch on the host — what the reference's caller
+        Repeated calls with the same (shape, dtype, crop) replay a CUDA graph captured at the end of the first such call (the caller's
+        warm-up call): the ~900 kernel launches of one forward then cost one graph launch on the host — what the reference's caller
         (run_stereo_matching's timing loop, model_utils.py:79-83; the calibration optimisers' ~100 calls, cem.py:55-72) sees
         through the unchanged nn.Module surface.  ``model.auto_graph = False`` (or S2M2_AUTO_GRAPH=0) keeps every call eager."""
         if (self.auto_graph and self.taps is None and img0.is_cuda and self.ops is not None and hasattr(self.ops, "lib")
@@ -507,16 +508,23 @@ class S2M2(nn.Module):
         key = (tuple(img0.shape), img0.dtype, img1.dtype, str(img0.device), None if crop_hw is None else tuple(int(v) for v in crop_hw),
                self.precision, self.use_positivity, self.refine_iter, self.output_upsample)
         ent = self._graphs.get(key)
-        if ent is None:                       # first call at this shape: eager (it also packs weights / builds tables)
-            self._graphs[key] = {"n": 1}
-            while len(self._graphs) > self.auto_graph_slots:       # a captured graph pins its whole activation pool: keep few
+        if ent is not None and "graph" in ent:
+            self._graphs[key] = self._graphs.pop(key)                  # most recently used last
+            ent["in0"].copy_(img0); ent["in1"].copy_(img1)
+            ent["graph"].replay()
+            return tuple(t.clone() for t in ent["out"])               # the graph's output buffers are overwritten by the next replay
+        if ent is None:
+            ent = self._graphs[key] = {"n": 0}
+            while len(self._graphs) > self.auto_graph_slots:           # a captured graph pins its whole activation pool: keep few
                 self._graphs.pop(next(iter(self._graphs)))
-            return self._forward_eager(img0, img1, crop_hw)
-        if "graph" not in ent:                # second call: capture
-            if tuple(img0.shape) != tuple(img1.shape):
-                return self._forward_eager(img0, img1, crop_hw)
+        res = self._forward_eager(img0, img1, crop_hw)                # (the first call also packs the weights / builds the tables)
+        ent["n"] += 1
+        if ent["n"] >= self.auto_graph_warm and tuple(img0.shape) == tuple(img1.shape):
+            # capture now, at the end of the warm-up call(s): the caller's NEXT call (run_stereo_matching's timed loop after its
+            # warm-up call, model_utils.py:69-70 of the demo) is already a replay
             dev = img0.device
-            ent["in0"], ent["in1"] = torch.empty_like(img0, memory_format=torch.contiguous_format), torch.empty_like(img1, memory_format=torch.contiguous_format)
+            ent["in0"] = torch.empty_like(img0, memory_format=torch.contiguous_format)
+            ent["in1"] = torch.empty_like(img1, memory_format=torch.contiguous_format)
             ent["in0"].copy_(img0); ent["in1"].copy_(img1)
             cur = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -527,12 +535,7 @@ class S2M2(nn.Module):
                     out = self._forward_eager(ent["in0"], ent["in1"], crop_hw)
             cur.wait_stream(side)
             ent["graph"], ent["out"] = g, out
-            g.replay()
-            return tuple(t.clone() for t in out)
-        self._graphs[key] = self._graphs.pop(key)                  # most recently used last
-        ent["in0"].copy_(img0); ent["in1"].copy_(img1)
-        ent["graph"].replay()
-        return tuple(t.clone() for t in ent["out"])               # the graph's output buffers are overwritten by the next replay
+        return res
 
     def _forward_eager(self, img0: torch.Tensor, img1: torch.Tensor, crop_hw=None):
         if self.ops is None:

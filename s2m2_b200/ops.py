@@ -61,7 +61,7 @@ EXPORTS = [
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
     "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_filter1x_crop", "s2m2b200_image_pad", "s2m2b200_last_error",
     "s2m2b200_preprocess_u8", "s2m2b200_stem_u8", "s2m2b200_confidence_score", "s2m2b200_disparity_to_points",
-    "s2m2b200_version", "s2m2b200_launch_count",
+    "s2m2b200_version", "s2m2b200_launch_count", "s2m2b200_set_plan_mode",
 ]
 
 
@@ -105,6 +105,7 @@ class CudaOps:
         self.attn_tc = os.environ.get("S2M2_ATTN_TC", "1") != "0"     # tcgen05 whole-row attention for the scan-line blocks
         self._pe = {}
         self._gn_work = {}
+        self._attn_work = {}
 
     # -- helpers
     def _chk(self, rc, name):
@@ -264,9 +265,11 @@ class CudaOps:
         work, wbytes = None, 0
         if pesum is None and self.attn_tc:
             wbytes = int(self.lib.s2m2b200_attention_workspace_bytes(S, N, heads, o.shape[3] // heads, _DT[qkv.dtype]))
-            if wbytes > 0:
-                wt = torch.empty(wbytes // 2, dtype=torch.float16, device=qkv.device)   # V^T scratch of the tcgen05 kernel
-                work = C.c_void_p(wt.data_ptr())
+            if wbytes > 0:      # (the whole-row kernel needs no scratch any more: a cached token buffer keeps the ABI's opt-in)
+                key = (str(qkv.device), wbytes)
+                if key not in self._attn_work:
+                    self._attn_work[key] = torch.empty(max(wbytes // 2, 8), dtype=torch.float16, device=qkv.device)
+                work = C.c_void_p(self._attn_work[key].data_ptr())
         if pesum is not None:
             px, py, ph, pw = pe[:4]
             ind = pe[4] if len(pe) > 4 and self.attn_tc else None

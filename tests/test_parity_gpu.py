@@ -349,8 +349,8 @@ def test_pipelined_runner_matches_direct_forward(in_dtype):
 
 
 def test_module_auto_graph_replay_is_bit_identical_to_eager():
-    """S2M2.forward replays a CUDA graph captured on the second call of a (shape, dtype, crop) — the path run_stereo_matching's
-    repeated calls take.  Every call must return exactly what the eager launches return, also after a shape change in between."""
+    """S2M2.forward replays a CUDA graph captured at the end of the first call of a (shape, dtype, crop) — the path
+    run_stereo_matching's repeated calls take.  Every call must return exactly what the eager launches return, also after a shape change in between."""
     C, NTR = 32, 1
     sd = random_state_dict(C, NTR, 0)
     m = _model(C, NTR, sd, precision="fp16")
