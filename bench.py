@@ -14,6 +14,8 @@ architecture, synthetic images — there is no network for checkpoints/datasets)
   e2e        the same metric through the public runtime call (s2m2_b200.runtime.PipelinedRunner.run) with HOST (pinned)
              inputs: H2D copy of both images and D2H read of disparity/occlusion/confidence inside the timed region, every
              step; the copies of neighbouring steps overlap the compute of the current one on a second stream.
+  e2e_cabi   (N=1) the same step through the handle-level C-ABI (s2m2b200_forward: C++ schedule, eager launches, host buffers in and
+             out, one synchronize per step) — what a host that is not Python gets.
   roofline   dominant kernel = the implicit-GEMM convolution; the heaviest conv shape of the model is timed
              alone with CUDA events; achieved = 2*M*N*K / time against MEASURED_PEAKS.json (burst figure); forward_frac =
              the whole forward (pairs/s x TFLOP/pair) against the sustained figure.
@@ -173,6 +175,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cabi", action="store_true", help="skip the handle-level C-ABI end-to-end leg (e2e_cabi)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -296,6 +299,40 @@ def main():
                       "note": "uint8 host images through PipelinedRunner(input_dtype=uint8).run (graph replay, overlapped copies), this rank only"}
             del ru8
 
+        # ---- the same end-to-end step through the handle-level C-ABI (s2m2b200_forward, host side in C++, eager launches — what a
+        # host that is not Python calls): per step pinned host images -> device, the forward, the three maps -> pinned host memory,
+        # one stream synchronize (no overlap between steps)
+        e2e_cabi = None
+        if rank == 0 and world == 1 and not args.no_cabi:
+            from s2m2_b200.host import HostForward
+            hf = HostForward(C, NTR, use_positivity=True, refine_iter=3, precision=args.precision)
+            hf.load_state_dict(model.state_dict())
+            dl, dr = torch.empty_like(left), torch.empty_like(right)
+            nc = max(2, min(args.steps, 5))
+
+            def cabi_run(n):
+                for _ in range(n):
+                    dl.copy_(left_h, non_blocking=True)
+                    dr.copy_(right_h, non_blocking=True)
+                    o = hf(dl, dr)
+                    for k in range(3):
+                        host_out[k].copy_(o[k], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+            cabi_run(2)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = hf.lib.s2m2b200_launch_count()
+            c0.record()
+            cabi_run(nc)
+            c1.record()
+            torch.cuda.synchronize()
+            e2e_cabi = {"value": B * nc / (c0.elapsed_time(c1) * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4,
+                        "d2h_bytes_per_step": 3 * B * H * W * 4, "steps": nc, "gpu_launches": int(hf.lib.s2m2b200_launch_count() - n0),
+                        "workspace_bytes": hf.workspace_bytes(B, H, W),
+                        "note": "s2m2b200_create/set_param/finalize_params/workspace_bytes/forward (include/s2m2b200.h): C++ schedule, eager "
+                                "launches, synchronous steps, this rank only"}
+            del hf, dl, dr
+            torch.cuda.empty_cache()
+
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         per_rank = [B * args.steps / (ms * 1e-3)]
         print(f"[rank {rank}/{world}] {per_rank[0]:.2f} pairs/s device-resident, {B * args.steps / (ms_e2e * 1e-3):.2f} pairs/s end to end "
@@ -401,6 +438,8 @@ def main():
         line["single_pair"] = single
     if e2e_u8:
         line["e2e_uint8"] = e2e_u8
+    if e2e_cabi:
+        line["e2e_cabi"] = e2e_cabi
     if tf:
         ach = value / world * tf
         line["roofline_forward"] = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",

@@ -232,6 +232,37 @@ int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int
                        void* stream);
 
 
+/* ---- the whole forward behind one handle (host side in C++: s2m2_b200/csrc/host_forward.cu) --------------------------------
+ * Replaces, for a host that is not Python, what s2m2.py:14-78 (constructor, my_load_state_dict) and s2m2.py:136-197 (forward)
+ * do around the ops above; model_utils.py:30-43 (load_model) and model_utils.py:72-83 (run_stereo_matching) are its callers.
+ *
+ *   create        feature_channels / num_transformer / use_positivity / output_upsample / refine_iter as S2M2.__init__
+ *                 (dim_expansion is 1, as load_model always passes); precision S2M2_F16 (tensor-core path) or S2M2_F32 (parity mode)
+ *   set_param     one state-dict entry under the reference's key (e.g. "refiner.gru.convz1.weight"): HOST fp32 data, copied
+ *   finalize      packs every layer into the layout its kernel reads and uploads the blob to the current device; fails naming the
+ *                 first missing / mis-shaped key
+ *   workspace     bytes of scratch one forward of (B, H, W) needs: the schedule is walked once in plan mode, nothing is launched;
+ *                 also builds the shape's constant tables (synchronous; call it outside stream capture).  < 0 on error
+ *   forward       left / right: DEVICE (B,3,H,W) planar images, fp32 (values 0..255) or uint8 (in_u8 != 0); H, W multiples of 32;
+ *                 out: DEVICE 3 x (B,1,Ho,Wo) fp32 planes [disparity | occlusion | confidence] (s2m2.py:197), Ho x Wo = H x W,
+ *                 2H x 2W with output_upsample, or crop_h x crop_w (the centre window image_crop keeps, image_utils.py:66-96) when
+ *                 crop_h, crop_w > 0; workspace: DEVICE scratch, 256-byte aligned.  Enqueues on `stream` only: no allocation, no
+ *                 synchronisation, capturable in a CUDA graph once the shape has been planned.
+ * All return 0 on success; s2m2b200_last_error() has the message otherwise. */
+typedef struct S2m2Model S2m2Model;
+int s2m2b200_create(int32_t feature_channels, int32_t num_transformer, int32_t use_positivity, int32_t output_upsample, int32_t refine_iter,
+                    int32_t precision, S2m2Model** out);
+int s2m2b200_set_param(S2m2Model* m, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+int s2m2b200_finalize_params(S2m2Model* m);
+int64_t s2m2b200_workspace_bytes(S2m2Model* m, int32_t B, int32_t H, int32_t W, int32_t in_u8, int32_t crop_h, int32_t crop_w);
+int s2m2b200_forward(S2m2Model* m, const void* left, const void* right, int32_t in_u8, int32_t B, int32_t H, int32_t W, int32_t crop_h,
+                     int32_t crop_w, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+void s2m2b200_destroy(S2m2Model* m);
+/* The packed blob's directory (tests): entry `index` of s2m2b200_packed_count; ptr is device memory when *on_device. */
+int64_t s2m2b200_packed_count(const S2m2Model* m);
+int s2m2b200_packed_entry(const S2m2Model* m, int64_t index, const char** name, const void** ptr, int64_t* bytes, int32_t* dtype,
+                          int32_t* on_device);
+
 const char* s2m2b200_last_error(void);
 /* Version / capability string, e.g. "s2m2b200 0.1 sm_100a tcgen05". */
 const char* s2m2b200_version(void);
@@ -240,6 +271,11 @@ int64_t s2m2b200_launch_count(void);
 /* Plan mode (thread-local; returns the previous value): while on, every op above runs its host-side checks and dispatch and
  * returns the code it would return, but enqueues nothing — how s2m2b200_workspace_bytes walks the forward schedule. */
 int s2m2b200_set_plan_mode(int on);
+/* Op trace (thread-local): between _begin and _end every op above appends one text line (name, tensor views, pointers, scalars);
+ * _note adds a caller's own line (allocations, named regions).  _end copies the text out and returns its full length. */
+int s2m2b200_trace_begin(void);
+void s2m2b200_trace_note(const char* text);
+int64_t s2m2b200_trace_end(char* buf, int64_t cap);
 
 #ifdef __cplusplus
 }

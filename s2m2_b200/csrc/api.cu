@@ -35,6 +35,35 @@ bool pdl_enabled() {   // S2M2_PDL=1 turns programmatic dependent launch on.  De
   return on != 0;
 }
 
+static thread_local bool g_trace_on = false;
+static thread_local char* g_trace = nullptr;
+static thread_local size_t g_trace_len = 0, g_trace_cap = 0;
+bool trace_on() { return g_trace_on; }
+void trace_append(const char* text) {
+  if (!g_trace_on) return;
+  const size_t n = strlen(text);
+  if (g_trace_len + n + 2 > g_trace_cap) {
+    g_trace_cap = (g_trace_cap ? g_trace_cap * 2 : (1 << 20)) + n + 2;
+    g_trace = (char*)realloc(g_trace, g_trace_cap);
+  }
+  memcpy(g_trace + g_trace_len, text, n);
+  g_trace_len += n;
+  g_trace[g_trace_len++] = '\n';
+  g_trace[g_trace_len] = 0;
+}
+void trace_fmt_tensor(char* buf, size_t cap, const S2m2Tensor* t) {
+  if (!t || !t->ptr) snprintf(buf, cap, " [null]");
+  else snprintf(buf, cap, " [%d,%d,%d,%d;ld%lld;%s;%p]", t->N, t->H, t->W, t->C, (long long)t->ld, t->dtype == S2M2_F16 ? "f16" : "f32", t->ptr);
+}
+void trace_fmt_conv(char* buf, size_t cap, const S2m2Conv* c) {
+  char x[160], x2[160], y[160], r[160], r2[160];
+  trace_fmt_tensor(x, sizeof(x), &c->x); trace_fmt_tensor(x2, sizeof(x2), &c->x2); trace_fmt_tensor(y, sizeof(y), &c->y);
+  trace_fmt_tensor(r, sizeof(r), &c->res); trace_fmt_tensor(r2, sizeof(r2), &c->res2);
+  snprintf(buf, cap, " x%s x2%s y%s res%s res2%s w %p %s bias %p k%dx%d s%d p%d,%d cout%d act%d shuf%d batch%d bs%lld,%lld,%lld impl%d emode%d from%d",
+           x, x2, y, r, r2, c->w, c->w_dtype == S2M2_F16 ? "f16" : "f32", (const void*)c->bias, c->KH, c->KW, c->stride, c->pad_h, c->pad_w,
+           c->Cout, c->act, c->shuffle2x2, c->batch, (long long)c->x_bs, (long long)c->w_bs, (long long)c->y_bs, c->impl, c->emode, c->res_from);
+}
+
 static CUresult encode_stub(CUtensorMap* m, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
   memset(m, 0, sizeof(*m));
@@ -60,6 +89,22 @@ using namespace s2m2;
 extern "C" {
 
 const char* s2m2b200_last_error(void) { return g_err; }
+int s2m2b200_trace_begin(void) {
+  g_trace_len = 0;
+  if (g_trace) g_trace[0] = 0;
+  g_trace_on = true;
+  return 0;
+}
+void s2m2b200_trace_note(const char* text) { trace_append(text); }
+int64_t s2m2b200_trace_end(char* buf, int64_t cap) {   // stops the trace; copies min(len, cap-1) bytes + NUL; returns the full length
+  g_trace_on = false;
+  if (buf && cap > 0) {
+    const size_t n = g_trace_len < (size_t)cap - 1 ? g_trace_len : (size_t)cap - 1;
+    if (n) memcpy(buf, g_trace, n);
+    buf[n] = 0;
+  }
+  return (int64_t)g_trace_len;
+}
 int s2m2b200_set_plan_mode(int on) {   // returns the previous value (thread-local)
   const int prev = g_plan;
   g_plan = on ? 1 : 0;
@@ -69,6 +114,7 @@ const char* s2m2b200_version(void) { return "s2m2b200 0.2 sm_100a (tcgen05 f16 i
 int64_t s2m2b200_launch_count(void) { return g_launches; }
 
 int s2m2b200_conv2d(const S2m2Conv* a, void* stream) {
+  S2M2_TRACE("conv2d", a);
   const S2m2Tensor &x = a->x, &y = a->y;
   S2M2_CHECK(x.ptr && y.ptr && a->w, "conv2d: null pointer");
   S2M2_CHECK(a->KH > 0 && a->KW > 0 && a->stride > 0 && a->Cout > 0, "conv2d: bad geometry");

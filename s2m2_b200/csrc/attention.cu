@@ -208,6 +208,7 @@ extern "C" int64_t s2m2b200_attention_workspace_bytes(int32_t S, int32_t N, int3
 extern "C" int s2m2b200_attention(const S2m2Tensor* qkv, const S2m2Tensor* out, int32_t S, int32_t N, int32_t heads,
                                   int32_t kv_shift, const float* pe_x, const float* pe_y, int32_t ph, int32_t pw,
                                   const S2m2Tensor* pesum, void* work, int64_t work_bytes, void* stream) {
+  S2M2_TRACE("attention", qkv, out, S, N, heads, kv_shift, pe_x, pe_y, ph, pw, pesum, work, work_bytes);
   const int C = out->C;
   S2M2_CHECK(qkv->C == 3 * C && C % heads == 0, "attention: qkv must have 3*C channels, C %% heads == 0");
   S2M2_CHECK(npix(*qkv) == (long long)S * N && npix(*out) == (long long)S * N, "attention: S*N != number of tokens");

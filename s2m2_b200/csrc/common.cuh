@@ -31,6 +31,40 @@ static inline bool plan_mode() { return g_plan != 0; }
 bool plan_without_device();
 void* plan_encode_stub();   // stands in for cuTensorMapEncodeTiled in a device-less plan: the maps are never used, only the return codes
 
+// ---- op trace -----------------------------------------------------------------------------------
+// While a trace is open (s2m2b200_trace_begin / _end, thread-local) every exported op appends one line: its name and its arguments
+// (tensor views as [N,H,W,C;ld;dtype;ptr], pointers, scalars).  tests/ compare the op sequence of the C++ host forward with the
+// Python schedule's this way, on the CPU, with plan mode on.
+bool trace_on();
+void trace_append(const char* text);
+void trace_fmt_tensor(char* buf, size_t cap, const S2m2Tensor* t);
+void trace_fmt_conv(char* buf, size_t cap, const S2m2Conv* c);
+struct TraceLine {
+  char buf[1024];
+  size_t n = 0;
+  void put(const char* s) {
+    while (*s && n + 1 < sizeof(buf)) buf[n++] = *s++;
+    buf[n] = 0;
+  }
+  void arg(const S2m2Tensor* t) { char b[160]; trace_fmt_tensor(b, sizeof(b), t); put(b); }
+  void arg(const S2m2Conv* c) { char b[900]; trace_fmt_conv(b, sizeof(b), c); put(b); }
+  void arg(const void* p) { char b[40]; snprintf(b, sizeof(b), " %p", p); put(b); }
+  void arg(long long v) { char b[40]; snprintf(b, sizeof(b), " %lld", v); put(b); }
+  void arg(int v) { arg((long long)v); }
+  void arg(long v) { arg((long long)v); }
+  void arg(float v) { char b[40]; snprintf(b, sizeof(b), " %.9g", (double)v); put(b); }
+};
+template <typename... A>
+static inline void trace_op(const char* name, A... a) {
+  if (!trace_on()) return;
+  TraceLine l;
+  l.put(name);
+  int dummy[] = {0, (l.arg(a), 0)...};
+  (void)dummy;
+  trace_append(l.buf);
+}
+#define S2M2_TRACE(...) s2m2::trace_op(__VA_ARGS__)
+
 #define S2M2_LAUNCH_OK(name)                                                        \
   do {                                                                              \
     if (s2m2::plan_mode()) break;                                                   \

@@ -546,6 +546,7 @@ static int stem_any(const TIn* left, const TIn* right, int32_t B, int32_t H, int
 extern "C" {
 
 int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* gamma, const float* beta, void* stream) {
+  S2M2_TRACE("layernorm", x, y, gamma, beta);
   S2M2_CHECK(x->C == y->C && npix(*x) == npix(*y), "layernorm: shape mismatch");
   S2M2_CHECK(x->C <= 1024, "layernorm: C=%d > 1024", x->C);
   S2M2_CHECK((gamma == nullptr) == (beta == nullptr), "layernorm: gamma/beta must both be given or both NULL");
@@ -562,6 +563,7 @@ int s2m2b200_layernorm(const S2m2Tensor* x, const S2m2Tensor* y, const float* ga
 
 int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups, const float* gamma, const float* beta,
                        double* work, void* stream) {
+  S2M2_TRACE("groupnorm", x, y, groups, gamma, beta, work);
   S2M2_CHECK(x->C == y->C && npix(*x) == npix(*y), "groupnorm: shape mismatch");
   S2M2_CHECK(groups > 0 && x->C % groups == 0 && groups <= 64, "groupnorm: bad groups");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "groupnorm: needs C,ld multiples of 4 and aligned bases");
@@ -596,6 +598,7 @@ int s2m2b200_groupnorm(const S2m2Tensor* x, const S2m2Tensor* y, int32_t groups,
 }
 
 int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
+  S2M2_TRACE("avgpool2", x, y);
   S2M2_CHECK(x->C == y->C && y->H == x->H / 2 && y->W == x->W / 2 && x->N == y->N && x->H % 2 == 0 && x->W % 2 == 0,
              "avgpool2: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "avgpool2: needs C,ld multiples of 4 and aligned bases");
@@ -614,6 +617,7 @@ int s2m2b200_avgpool2(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
 }
 
 int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) {
+  S2M2_TRACE("upsample2x", x, y);
   S2M2_CHECK(x->C == y->C && y->H == x->H * 2 && y->W == x->W * 2 && x->N == y->N, "upsample2x: shape mismatch");
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "upsample2x: needs C,ld multiples of 4 and aligned bases");
   if (h8_ok(*x) && h8_ok(*y)) {
@@ -641,6 +645,7 @@ static int ew_check(const S2m2Tensor* o, const S2m2Tensor* const* ins, int n, co
 
 int s2m2b200_gate_blend(const S2m2Tensor* f, const S2m2Tensor* g, const S2m2Tensor* z0, const S2m2Tensor* z1,
                         const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("gate_blend", f, g, z0, z1, out);
   const S2m2Tensor* ins[4] = {f, g, z0, z1};
   if (int r = ew_check(out, ins, 4, "gate_blend")) return r;
   long long total4 = npix(*out) * (out->C / 4);
@@ -650,6 +655,7 @@ int s2m2b200_gate_blend(const S2m2Tensor* f, const S2m2Tensor* g, const S2m2Tens
 }
 
 int s2m2b200_copy_channels(const S2m2Tensor* src, const S2m2Tensor* dst, void* stream) {
+  S2M2_TRACE("copy_channels", src, dst);
   const S2m2Tensor* ins[1] = {src};
   if (int r = ew_check(dst, ins, 1, "copy_channels")) return r;
   long long total4 = npix(*dst) * (dst->C / 4);
@@ -659,6 +665,7 @@ int s2m2b200_copy_channels(const S2m2Tensor* src, const S2m2Tensor* dst, void* s
 }
 
 int s2m2b200_unary(const S2m2Tensor* x, const S2m2Tensor* y, int32_t act, void* stream) {
+  S2M2_TRACE("unary", x, y, act);
   const S2m2Tensor* ins[1] = {x};
   if (int r = ew_check(y, ins, 1, "unary")) return r;
   long long total4 = npix(*y) * (y->C / 4);
@@ -668,6 +675,7 @@ int s2m2b200_unary(const S2m2Tensor* x, const S2m2Tensor* y, int32_t act, void* 
 }
 
 int s2m2b200_mul(const S2m2Tensor* a, const S2m2Tensor* b, const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("mul", a, b, out);
   const S2m2Tensor* ins[2] = {a, b};
   if (int r = ew_check(out, ins, 2, "mul")) return r;
   long long total4 = npix(*out) * (out->C / 4);
@@ -677,6 +685,7 @@ int s2m2b200_mul(const S2m2Tensor* a, const S2m2Tensor* b, const S2m2Tensor* out
 }
 
 int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tensor* h, void* stream) {
+  S2M2_TRACE("gru_update", z, q, h);
   const S2m2Tensor* ins[2] = {z, q};
   if (int r = ew_check(h, ins, 2, "gru_update")) return r;
   long long total4 = npix(*h) * (h->C / 4);
@@ -687,24 +696,29 @@ int s2m2b200_gru_update(const S2m2Tensor* z, const S2m2Tensor* q, const S2m2Tens
 
 int s2m2b200_preprocess(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
                         void* stream) {
+  S2M2_TRACE("preprocess", left, right, B, H, W, out);
   return preprocess_any(left, right, B, H, W, out, stream);
 }
 int s2m2b200_preprocess_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const S2m2Tensor* out,
                            void* stream) {
+  S2M2_TRACE("preprocess_u8", left, right, B, H, W, out);
   return preprocess_any(left, right, B, H, W, out, stream);
 }
 
 int s2m2b200_stem(const float* left, const float* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                   const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("stem", left, right, B, H, W, w0, b0, w1, b1, out);
   return stem_any(left, right, B, H, W, w0, b0, w1, b1, out, stream);
 }
 int s2m2b200_stem_u8(const uint8_t* left, const uint8_t* right, int32_t B, int32_t H, int32_t W, const float* w0, const float* b0,
                      const float* w1, const float* b1, const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("stem_u8", left, right, B, H, W, w0, b0, w1, b1, out);
   return stem_any(left, right, B, H, W, w0, b0, w1, b1, out, stream);
 }
 
 int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* wd, const float* bd, const float* wr,
                            const float* br, const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("mask1x_inputs", up, rgb, wd, bd, wr, br, out);
   S2M2_CHECK(rgb->C == 3 && out->C == 32 && npix(*rgb) == npix(*out) && vec4_ok(*out) && aligned(up, 16),
              "mask1x_inputs: rgb (B,H,W,3), out a 32-channel 4-aligned view, up 16-byte aligned");
   Mask1xW hw;   // wd/bd/wr/br are HOST pointers (2.4 KB of weights as a kernel parameter)
@@ -716,6 +730,7 @@ int s2m2b200_mask1x_inputs(const float* up, const S2m2Tensor* rgb, const float* 
 }
 
 int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n, const S2m2Tensor* out, void* stream) {
+  S2M2_TRACE("global_refiner_prep", disp, conf, n, out);
   S2M2_CHECK(out->C == 2 && npix(*out) == n, "global_refiner_prep: output must be a 2-channel view of npix pixels");
   launch_k(gr_prep_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, n, tv(*out));
   S2M2_LAUNCH_OK("global_refiner_prep");
@@ -724,6 +739,7 @@ int s2m2b200_global_refiner_prep(const float* disp, const float* conf, int64_t n
 
 int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* upd, int64_t upd_ld, int64_t n, int32_t pos,
                                   void* stream) {
+  S2M2_TRACE("global_refiner_merge", disp, conf, upd, upd_ld, n, pos);
   S2M2_CHECK(upd_ld >= 1, "global_refiner_merge: bad upd_ld");
   launch_k(gr_merge_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, upd, upd_ld, n, pos);
   S2M2_LAUNCH_OK("global_refiner_merge");
@@ -731,6 +747,7 @@ int s2m2b200_global_refiner_merge(float* disp, const float* conf, const float* u
 }
 
 int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const float* occ, int64_t n, float* small, void* stream) {
+  S2M2_TRACE("local_refiner_prep", disp, conf, occ, n, small);
   S2M2_CHECK(aligned(small, 16), "local_refiner_prep: small must be 16-byte aligned");
   launch_k(lr_prep_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, occ, n, (float4*)small);
   S2M2_LAUNCH_OK("local_refiner_prep");
@@ -739,6 +756,7 @@ int s2m2b200_local_refiner_prep(const float* disp, const float* conf, const floa
 
 int s2m2b200_local_refiner_update(float* disp, float* conf, float* occ, const float* small, const float* upd, int64_t upd_ld,
                                   int32_t B, int32_t h, int32_t w, int32_t pos, void* stream) {
+  S2M2_TRACE("local_refiner_update", disp, conf, occ, small, upd, upd_ld, B, h, w, pos);
   long long n = (long long)B * h * w;
   S2M2_CHECK(upd_ld >= 3, "local_refiner_update: upd needs >= 3 channels");
   launch_k(lr_update_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, disp, conf, occ, (const float4*)small, upd, upd_ld, n, w, pos);

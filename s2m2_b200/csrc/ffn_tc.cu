@@ -710,6 +710,7 @@ static int mlp2_dispatch(const S2m2Tensor* x, const S2m2Tensor* res, const S2m2T
 // returns 0 = launched, 1 = shape / dtype not supported by the fused kernel (caller runs LayerNorm + two conv2d), < 0 = error
 extern "C" int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void* w0, const float* b0, const void* w2, const float* b2,
                             int32_t w_dtype, void* stream) {
+  S2M2_TRACE("ffn", x, y, w0, b0, w2, b2, w_dtype);
   const int C = x->C;
   static const int force_v1 = getenv("S2M2_FFN_V1") ? atoi(getenv("S2M2_FFN_V1")) : 0;
   if (!force_v1 && C <= 256) {   // two tiles in flight; the residual is x itself
@@ -744,5 +745,6 @@ extern "C" int s2m2b200_ffn(const S2m2Tensor* x, const S2m2Tensor* y, const void
 // (attentions.py:273-281) summed with the 3x3 branch's output `res`.  0 = launched, 1 = not applicable, < 0 = error.
 extern "C" int s2m2b200_mlp2(const S2m2Tensor* x, const S2m2Tensor* res, const S2m2Tensor* y, const void* w0, const float* b0,
                              const void* w2, const float* b2, int32_t w_dtype, int32_t layernorm, int32_t act, void* stream) {
+  S2M2_TRACE("mlp2", x, res, y, w0, b0, w2, b2, w_dtype, layernorm, act);
   return mlp2_dispatch(x, res, y, w0, b0, w2, b2, w_dtype, layernorm, act, (cudaStream_t)stream);
 }

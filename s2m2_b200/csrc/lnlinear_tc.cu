@@ -259,6 +259,7 @@ using namespace s2m2;
 // returns 0 = launched, 1 = not applicable (caller runs layernorm + conv2d), < 0 = error
 extern "C" int s2m2b200_ln_linear(const S2m2Tensor* x, const S2m2Tensor* y, const void* w, const float* bias, int32_t w_dtype,
                                   void* stream) {
+  S2M2_TRACE("ln_linear", x, y, w, bias, w_dtype);
   const int C = x->C, N = y->C;
   if (x->dtype != S2M2_F16 || y->dtype != S2M2_F16 || w_dtype != S2M2_F16) return 1;
   if (!(C == 128 || C == 192 || C == 256)) return 1;

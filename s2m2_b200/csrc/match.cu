@@ -421,6 +421,7 @@ extern "C" {
 
 int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t w, float* disp, float* conf, float* occ,
                                  int32_t* amax, int32_t use_positivity, int32_t iters, void* stream) {
+  S2M2_TRACE("sinkhorn_softargmax", cv, B, h, w, disp, conf, occ, amax, use_positivity, iters);
   S2M2_CHECK(w >= 8 && w <= 5000 && iters >= 1, "sinkhorn: bad w=%d / iters=%d (8 <= w <= 5000)", w, iters);
   // the matrix-resident cluster kernel (sinkhorn_cluster.cu) takes every width whose scan-line fits a cluster's shared memory
   // (w <= 639 with positivity); S2M2_SK_IMPL=1 forces the streaming kernel below
@@ -436,6 +437,7 @@ int s2m2b200_sinkhorn_softargmax(const float* cv, int32_t B, int32_t h, int32_t 
 }
 
 int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h, int32_t w, float* out, void* stream) {
+  S2M2_TRACE("cv_lookup", cv, disp, B, h, w, out);
   long long n = (long long)B * h * w;
   long long g = (n * 18 + 255) / 256;
   launch_k(cv_lookup_kernel, (int)(g > 148 * 64 ? 148 * 64 : g), 256, 0, (cudaStream_t)stream, cv, disp, n, w, out);
@@ -445,6 +447,7 @@ int s2m2b200_cv_lookup(const float* cv, const float* disp, int32_t B, int32_t h,
 
 int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float* conf, const float* logits, int32_t logits_ld,
                                int32_t B, int32_t h, int32_t w, float* up, void* stream) {
+  S2M2_TRACE("upsample4x_convex", disp, occ, conf, logits, logits_ld, B, h, w, up);
   S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "upsample4x_convex: up must be 16-byte aligned, logits_ld >= 9");
   long long n = 16LL * B * h * w;
   long long g = (n + 255) / 256;
@@ -455,6 +458,7 @@ int s2m2b200_upsample4x_convex(const float* disp, const float* occ, const float*
 
 int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, float* out,
                       int32_t upsample2, void* stream) {
+  S2M2_TRACE("filter1x", up, logits, logits_ld, B, H, W, out, upsample2);
   S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "filter1x: up must be 16-byte aligned, logits_ld >= 9");
   if (upsample2) {
     long long n2 = 4LL * B * H * W;
@@ -473,6 +477,7 @@ int s2m2b200_filter1x(const float* up, const float* logits, int32_t logits_ld, i
 
 int s2m2b200_filter1x_crop(const float* up, const float* logits, int32_t logits_ld, int32_t B, int32_t H, int32_t W, int32_t crop_h,
                            int32_t crop_w, float* out, void* stream) {
+  S2M2_TRACE("filter1x_crop", up, logits, logits_ld, B, H, W, crop_h, crop_w, out);
   S2M2_CHECK(aligned(up, 16) && logits_ld >= 9, "filter1x_crop: up must be 16-byte aligned, logits_ld >= 9");
   S2M2_CHECK(crop_h > 0 && crop_w > 0 && crop_h <= H && crop_w <= W, "filter1x_crop: bad crop %dx%d of %dx%d", crop_h, crop_w, H, W);
   const int y0 = (H - crop_h) / 2, x0 = (W - crop_w) / 2;          // image_crop drops floor(d/2) rows / columns in front
@@ -486,6 +491,7 @@ int s2m2b200_filter1x_crop(const float* up, const float* logits, int32_t logits_
 
 int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int32_t W, int32_t factor, float* out, float* work,
                        void* stream) {
+  S2M2_TRACE("image_pad", img, is_u8, B, H, W, factor, out, work);
   S2M2_CHECK(factor > 0 && H >= factor && W >= factor, "image_pad: the image must be at least factor x factor");
   const int Hn = (H + factor - 1) / factor * factor, Wn = (W + factor - 1) / factor * factor;
   const int hs = (Hn - H) / 2, ws = (Wn - W) / 2;                   // image_utils.py:47-52: floor(pad/2) in front
@@ -512,6 +518,7 @@ int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int
 
 int s2m2b200_confidence_score(const float* conf, int32_t B, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w, int32_t margin,
                               float* out, void* stream) {
+  S2M2_TRACE("confidence_score", conf, B, H, W, crop_h, crop_w, margin, out);
   S2M2_CHECK(crop_h > 0 && crop_w > 0 && crop_h <= H && crop_w <= W && margin >= 0, "confidence_score: bad crop / margin");
   const int ys = (H - crop_h) / 2, xs = (W - crop_w) / 2;     // image_crop drops floor(d/2) rows/columns in front
   const int y0 = ys + margin, y1 = ys + crop_h - margin, x0 = xs + margin, x1 = xs + crop_w - margin;
@@ -524,6 +531,7 @@ int s2m2b200_confidence_score(const float* conf, int32_t B, int32_t H, int32_t W
 int s2m2b200_disparity_to_points(const float* disp, const float* conf, const float* occ, int32_t B, int32_t H, int32_t W, float fx, float cx,
                                  float cy, float baseline, float doffs, float depth_scale, float depth_trunc, float* xyz, uint8_t* valid,
                                  void* stream) {
+  S2M2_TRACE("disparity_to_points", disp, conf, occ, B, H, W, fx, cx, cy, baseline, doffs, depth_scale, depth_trunc, xyz, valid);
   S2M2_CHECK(fx > 0.f && depth_scale > 0.f, "disparity_to_points: fx and depth_scale must be positive");
   const long long n = (long long)B * H * W;
   const long long g = (n + 255) / 256;

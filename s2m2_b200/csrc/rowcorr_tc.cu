@@ -257,6 +257,7 @@ extern "C" int64_t s2m2b200_row_corr_workspace_bytes(int32_t B, int32_t h, int32
 // s2m2b200_row_corr_workspace_bytes.  Returns 0 = launched, 1 = not applicable (caller: layernorm + the fp32 CUDA-core GEMM).
 extern "C" int s2m2b200_row_corr(const S2m2Tensor* f, const float* gamma, const float* beta, float* cv, void* work, int64_t work_bytes,
                                  void* stream) {
+  S2M2_TRACE("row_corr", f, gamma, beta, cv, work, work_bytes);
   const int C = f->C, w = f->W, h = f->H, B = f->N / 2;
   if (f->dtype != S2M2_F16 || f->N % 2 || !work) return 1;
   const int64_t need = s2m2b200_row_corr_workspace_bytes(B, h, w, C);

@@ -410,7 +410,7 @@ int sinkhorn_cluster_launch(const float* cv, int B, int h, int w, float* disp, f
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  (void)cudaLaunchKernelEx(&cfg, kernel, p);
+  if (!plan_mode()) (void)cudaLaunchKernelEx(&cfg, kernel, p);
   S2M2_LAUNCH_OK("sinkhorn_cluster");
   return 0;
 }

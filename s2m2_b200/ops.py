@@ -50,6 +50,8 @@ def load_library():
     lib.s2m2b200_attention_workspace_bytes.restype = C.c_int64
     lib.s2m2b200_pe_indicator_bytes.restype = C.c_int64
     lib.s2m2b200_row_corr_workspace_bytes.restype = C.c_int64
+    lib.s2m2b200_trace_end.restype = C.c_int64
+    lib.s2m2b200_trace_note.restype = None
     _lib = lib
     return lib
 
@@ -62,6 +64,10 @@ EXPORTS = [
     "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_filter1x_crop", "s2m2b200_image_pad", "s2m2b200_last_error",
     "s2m2b200_preprocess_u8", "s2m2b200_stem_u8", "s2m2b200_confidence_score", "s2m2b200_disparity_to_points",
     "s2m2b200_version", "s2m2b200_launch_count", "s2m2b200_set_plan_mode",
+    "s2m2b200_trace_begin", "s2m2b200_trace_note", "s2m2b200_trace_end",
+    # the whole forward behind one handle (host side in C++; bound in s2m2_b200/host.py)
+    "s2m2b200_create", "s2m2b200_set_param", "s2m2b200_finalize_params", "s2m2b200_workspace_bytes", "s2m2b200_forward", "s2m2b200_destroy",
+    "s2m2b200_packed_count", "s2m2b200_packed_entry",
 ]
 
 
@@ -85,8 +91,7 @@ class CudaOps:
     """The product's op backend: every method enqueues hand-written CUDA kernels on the current stream."""
 
     def __init__(self, conv_impl: int = None):
-        if not torch.cuda.is_available():
-            raise RuntimeError("s2m2_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._check_device()
         self.lib = load_library()
         if conv_impl is None:
             conv_impl = int(os.environ.get("S2M2_CONV_IMPL", "0"))
@@ -108,6 +113,14 @@ class CudaOps:
         self._attn_work = {}
 
     # -- helpers
+    def _check_device(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("s2m2_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+    def _scratch(self, numel, dtype, device, zero=False):
+        """Op-internal scratch / cached work buffers (one place, so that the plan-mode harness in tests/ sees them)."""
+        return (torch.zeros if zero else torch.empty)(numel, dtype=dtype, device=device)
+
     def _chk(self, rc, name):
         if rc != 0:
             raise RuntimeError(f"{name} failed ({rc}): {self.lib.s2m2b200_last_error().decode()}")
@@ -251,7 +264,7 @@ class CudaOps:
         nb = int(self.lib.s2m2b200_row_corr_workspace_bytes(B, h, w, f.shape[3]))
         if nb == 0 or not cv.is_contiguous() or cv.dtype != torch.float32:
             return False
-        work = torch.empty(nb // 2, dtype=torch.float16, device=f.device)
+        work = self._scratch(nb // 2, torch.float16, f.device)
         rc = self.lib.s2m2b200_row_corr(C.byref(tview(f)), C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), C.c_void_p(cv.data_ptr()),
                                         C.c_void_p(work.data_ptr()), C.c_int64(nb), self._stream())
         if rc == 1:
@@ -268,7 +281,7 @@ class CudaOps:
             if wbytes > 0:      # (the whole-row kernel needs no scratch any more: a cached token buffer keeps the ABI's opt-in)
                 key = (str(qkv.device), wbytes)
                 if key not in self._attn_work:
-                    self._attn_work[key] = torch.empty(max(wbytes // 2, 8), dtype=torch.float16, device=qkv.device)
+                    self._attn_work[key] = self._scratch(max(wbytes // 2, 8), torch.float16, qkv.device)
                 work = C.c_void_p(self._attn_work[key].data_ptr())
         if pesum is not None:
             px, py, ph, pw = pe[:4]
@@ -294,7 +307,7 @@ class CudaOps:
         nblk = (x.shape[1] * x.shape[2] + 255) // 256
         key = (x.shape[0], groups, nblk, str(x.device))
         if key not in self._gn_work:
-            self._gn_work[key] = torch.zeros(2 * x.shape[0] * groups * (1 + nblk), dtype=torch.float64, device=x.device)
+            self._gn_work[key] = self._scratch(2 * x.shape[0] * groups * (1 + nblk), torch.float64, x.device, zero=True)
         work = self._gn_work[key]
         xt, yt = tview(x), tview(out)
         self._chk(self.lib.s2m2b200_groupnorm(C.byref(xt), C.byref(yt), groups, C.c_void_p(gamma.data_ptr()),
