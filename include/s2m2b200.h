@@ -228,6 +228,14 @@ int s2m2b200_filter1x_crop(const float* up, const float* logits, int32_t logits_
  * (B,3,H,W) uint8 / fp32 image to multiples of `factor`, the padding filled with the reference's blurred copy
  * (adaptive_avg_pool2d to (H/factor, W/factor) of the zero-padded image, bilinear back up), the original pasted over it.
  * out: (B,3,Hn,Wn) fp32, work: 3*B*(H/factor)*(W/factor) floats of device scratch. */
+/* Stereo rectification of uint8 images: cv2.remap(src, mapx, mapy, INTER_LINEAR, border constant 0), bit-exact with OpenCV's
+ * fixed-point 8-bit path (image_utils.py:108-136 rectify_images; the calibration optimisers call it per candidate rotation,
+ * calibration/base.py:15-36, cem.py:64-72).  src: DEVICE (Hs,Ws,3) interleaved uint8 as cv2 reads it; source n starts at
+ * src + n*src_stride bytes (0 = all N outputs sample the same image: N candidate rectifications of one frame); mapx / mapy: DEVICE
+ * (N,Hd,Wd) fp32 source coordinates (cv2.initUndistortRectifyMap, CV_32FC1); dst: DEVICE uint8, planar (N,3,Hd,Wd) — what
+ * s2m2b200_forward / S2M2.forward take — when planar != 0, else interleaved (N,Hd,Wd,3) like cv2's result. */
+int s2m2b200_remap_u8(const uint8_t* src, int64_t src_stride, int32_t Hs, int32_t Ws, const float* mapx, const float* mapy, int32_t N,
+                      int32_t Hd, int32_t Wd, uint8_t* dst, int32_t planar, void* stream);
 int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int32_t W, int32_t factor, float* out, float* work,
                        void* stream);
 
@@ -248,6 +256,9 @@ int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int
  *                 2H x 2W with output_upsample, or crop_h x crop_w (the centre window image_crop keeps, image_utils.py:66-96) when
  *                 crop_h, crop_w > 0; workspace: DEVICE scratch, 256-byte aligned.  Enqueues on `stream` only: no allocation, no
  *                 synchronisation, capturable in a CUDA graph once the shape has been planned.
+ *   graph mode    off by default.  On: forward captures the launches of a shape into a CUDA graph the first time it sees a set of
+ *                 buffer addresses (left, right, out, workspace) and replays it on later calls with the same addresses — one graph
+ *                 launch instead of ~900 kernel launches (a host that reuses its buffers; other addresses re-capture).
  * All return 0 on success; s2m2b200_last_error() has the message otherwise. */
 typedef struct S2m2Model S2m2Model;
 int s2m2b200_create(int32_t feature_channels, int32_t num_transformer, int32_t use_positivity, int32_t output_upsample, int32_t refine_iter,
@@ -257,6 +268,7 @@ int s2m2b200_finalize_params(S2m2Model* m);
 int64_t s2m2b200_workspace_bytes(S2m2Model* m, int32_t B, int32_t H, int32_t W, int32_t in_u8, int32_t crop_h, int32_t crop_w);
 int s2m2b200_forward(S2m2Model* m, const void* left, const void* right, int32_t in_u8, int32_t B, int32_t H, int32_t W, int32_t crop_h,
                      int32_t crop_w, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int s2m2b200_set_graph_mode(S2m2Model* m, int32_t on);
 void s2m2b200_destroy(S2m2Model* m);
 /* The packed blob's directory (tests): entry `index` of s2m2b200_packed_count; ptr is device memory when *on_device. */
 int64_t s2m2b200_packed_count(const S2m2Model* m);

@@ -20,6 +20,29 @@ def image_pad(img: torch.Tensor, factor: int = 32) -> torch.Tensor:
     return out
 
 
+def remap_u8(src, mapx, mapy):
+    """cv2.remap(src uint8 (H,W,3), mapx, mapy float32, INTER_LINEAR, BORDER_CONSTANT 0) restated in numpy — what
+    image_utils.py:108-136 (rectify_images) computes.  OpenCV's 8-bit bilinear remap is fixed point (imgproc remap.cpp /
+    imgwarp initInterTab2D): coordinates rounded half-even to 1/32 pixel, weights (32-fy)(32-fx)*32 ... on a 2^15 scale with the
+    integer-coordinate entry [32767, 0, 0, 1], result (sum + 2^14) >> 15, out-of-image taps read 0.  tests/test_post_cpu.py pins this
+    against cv2.remap itself (cv2 is in the image) and tests/golden/remap_u8.npz holds cv2's output for the GPU test."""
+    import numpy as np
+    H, W, _ = src.shape
+    sx = np.rint(mapx.astype(np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(mapy.astype(np.float32) * np.float32(32)).astype(np.int64)
+    ix, iy = np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)
+    fx, fy = sx & 31, sy & 31
+    w = np.stack([(32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32], -1)
+    w[(fx == 0) & (fy == 0)] = np.array([32767, 0, 0, 1])
+    acc = np.zeros(mapx.shape + (3,), np.int64)
+    for k, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        y, x = iy + dy, ix + dx
+        ok = (y >= 0) & (y < H) & (x >= 0) & (x < W)
+        v = np.where(ok[..., None], src[np.clip(y, 0, H - 1), np.clip(x, 0, W - 1)].astype(np.int64), 0)
+        acc += v * w[..., k][..., None]
+    return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
 def image_crop(img: torch.Tensor, img_shape):
     """image_utils.py:66-96: centre crop of the last two dims, floor(d/2) dropped in front, the rest behind."""
     H, W = img.shape[-2:]

@@ -124,6 +124,9 @@ struct Plan {   // what s2m2b200_workspace_bytes leaves behind for one (B, H, W,
   bool consts_on_device = false;
   size_t pe_x = 0, pe_y = 0, pe_ind = 0, attn_work = 0, consts_bytes = 0, ind_bytes = 0;
   bool has_ind = false;
+  // graph mode (s2m2b200_set_graph_mode): the forward of this shape captured once for one set of buffer addresses
+  cudaGraphExec_t exec = nullptr;
+  const void *g_left = nullptr, *g_right = nullptr, *g_out = nullptr, *g_work = nullptr;
 };
 
 }  // namespace host
@@ -158,13 +161,17 @@ struct S2m2Model {
   ConvW u4_x, u4_y, u4_c0, u4_c2, u1_ctx, u1_c0, u1_c2;
   std::vector<ConvW*> all_convs;
   std::map<ShapeKey, Plan> plans;
+  bool graph_mode = false;
+  cudaStream_t cap_stream = nullptr;   // graph mode captures on a stream of its own (the caller's may be the legacy default stream)
 
   ~S2m2Model() {
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     if (blob) {
       if (blob_on_device) cudaFree(blob);
       else free(blob);
     }
     for (auto& kv : plans) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       if (!kv.second.consts) continue;
       if (kv.second.consts_on_device) cudaFree(kv.second.consts);
       else free(kv.second.consts);
@@ -1068,7 +1075,7 @@ static void resolve(S2m2Model& m) {
   }
 }
 
-static const Plan& make_plan(S2m2Model& m, const ShapeKey& key) {
+static Plan& make_plan(S2m2Model& m, const ShapeKey& key) {
   auto it = m.plans.find(key);
   if (it != m.plans.end()) return it->second;
   const int B = key.B, H = key.H, W = key.W;
@@ -1211,6 +1218,12 @@ int s2m2b200_finalize_params(S2m2Model* m) {
   S2M2_GUARD_END(-1)
 }
 
+int s2m2b200_set_graph_mode(S2m2Model* m, int32_t on) {
+  S2M2_CHECK(m, "set_graph_mode: null model");
+  m->graph_mode = on != 0;
+  return 0;
+}
+
 int64_t s2m2b200_packed_count(const S2m2Model* m) { return m && m->finalized ? (int64_t)m->dir.size() : -1; }
 
 int s2m2b200_packed_entry(const S2m2Model* m, int64_t index, const char** name, const void** ptr, int64_t* bytes, int32_t* dtype, int32_t* on_device) {
@@ -1255,13 +1268,47 @@ int s2m2b200_forward(S2m2Model* m, const void* left, const void* right, int32_t 
   S2M2_CHECK(((uintptr_t)workspace & 255) == 0, "forward: the workspace must be 256-byte aligned");
   S2M2_GUARD_BEGIN
   const ShapeKey key{B, H, W, in_u8 ? 1 : 0, crop_h, crop_w};
-  const Plan& pl = make_plan(*m, key);   // cached after s2m2b200_workspace_bytes; first use of a shape plans here (not capturable)
+  Plan& pl = make_plan(*m, key);   // cached after s2m2b200_workspace_bytes; first use of a shape plans here (not capturable)
   S2M2_CHECK((size_t)workspace_bytes >= pl.workspace, "forward: workspace of %lld bytes, %zu needed (s2m2b200_workspace_bytes)", (long long)workspace_bytes, pl.workspace);
-  Run run(*m, stream, false);
+  cudaStream_t cs = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool own_graph = m->graph_mode && cudaStreamIsCapturing(cs, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+  if (own_graph && pl.exec && pl.g_left == left && pl.g_right == right && pl.g_out == out && pl.g_work == workspace) {
+    S2M2_CHECK(cudaGraphLaunch(pl.exec, cs) == cudaSuccess, "forward: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  if (own_graph && !m->cap_stream)
+    S2M2_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) == cudaSuccess, "forward: cudaStreamCreate failed");
+  Run run(*m, own_graph ? (void*)m->cap_stream : stream, false);
   run.pl = &pl;
   run.arena.base = (char*)workspace;
   run.arena.cap = (size_t)workspace_bytes;
-  run.forward(left, right, in_u8 != 0, B, H, W, crop_h, crop_w, out);
+  if (!own_graph) {
+    run.forward(left, right, in_u8 != 0, B, H, W, crop_h, crop_w, out);
+    return 0;
+  }
+  // graph mode: capture this shape's ~900 launches once for these buffers, then replay (the addresses are baked into the graph;
+  // a call with other buffers re-captures)
+  if (pl.exec) {
+    cudaGraphExecDestroy(pl.exec);
+    pl.exec = nullptr;
+  }
+  S2M2_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess, "forward: cudaStreamBeginCapture failed: %s",
+             cudaGetErrorString(cudaGetLastError()));
+  cudaGraph_t graph = nullptr;
+  try {
+    run.forward(left, right, in_u8 != 0, B, H, W, crop_h, crop_w, out);
+  } catch (...) {
+    cudaStreamEndCapture(m->cap_stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  S2M2_CHECK(cudaStreamEndCapture(m->cap_stream, &graph) == cudaSuccess && graph, "forward: cudaStreamEndCapture failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const cudaError_t ie = cudaGraphInstantiate(&pl.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  S2M2_CHECK(ie == cudaSuccess, "forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+  pl.g_left = left; pl.g_right = right; pl.g_out = out; pl.g_work = workspace;
+  S2M2_CHECK(cudaGraphLaunch(pl.exec, cs) == cudaSuccess, "forward: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
   S2M2_GUARD_END(-1)
 }

@@ -409,6 +409,43 @@ __global__ void pad_fill_kernel(const T* __restrict__ img, const float* __restri
   }
 }
 
+// ---- stereo rectification: cv2.remap(uint8, INTER_LINEAR, BORDER_CONSTANT 0), bit-exact ------------------------------------
+// image_utils.py:108-136 (rectify_images) applies cv2.remap with float32 maps to both uint8 images; the calibration optimisers do
+// that for every candidate rotation (base.py:15-36, cem.py:64-72).  OpenCV's 8-bit bilinear remap is fixed point: the map is
+// rounded to 1/32 pixel (round-half-even of x*32), the four weights are (32-fy)(32-fx)*32 ... on a 2^15 scale, the result is
+// (sum + 2^14) >> 15; taps outside the source read the border value 0.  At integer coordinates the table entry is
+// [32767, 0, 0, 1] (saturate_cast<short>(32768) plus OpenCV's sum correction).  dst is planar (N,3,Hd,Wd) — what the forward's
+// uint8 ingest takes — or interleaved (N,Hd,Wd,3) like cv2's output.
+__global__ void remap_u8_kernel(const uint8_t* __restrict__ src, long long src_stride, int Hs, int Ws, const float* __restrict__ mapx,
+                                const float* __restrict__ mapy, long long n_pix, int Hd, int Wd, uint8_t* __restrict__ dst, int planar) {
+  pdl_sync();
+  const long long hw = (long long)Hd * Wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, r = i - n * hw;
+    const int sx = __float2int_rn(mapx[i] * 32.f), sy = __float2int_rn(mapy[i] * 32.f);
+    int ix = sx >> 5, iy = sy >> 5;
+    ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);     // saturate_cast<short>
+    iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
+    const int fx = sx & 31, fy = sy & 31;
+    int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+    const uint8_t* S = src + n * src_stride;
+    int acc[3] = {0, 0, 0};
+    const bool y0 = iy >= 0 && iy < Hs, y1 = iy + 1 >= 0 && iy + 1 < Hs, x0 = ix >= 0 && ix < Ws, x1 = ix + 1 >= 0 && ix + 1 < Ws;
+    if (y0 && x0) { const uint8_t* p = S + ((long long)iy * Ws + ix) * 3; acc[0] += p[0] * w00; acc[1] += p[1] * w00; acc[2] += p[2] * w00; }
+    if (y0 && x1) { const uint8_t* p = S + ((long long)iy * Ws + ix + 1) * 3; acc[0] += p[0] * w01; acc[1] += p[1] * w01; acc[2] += p[2] * w01; }
+    if (y1 && x0) { const uint8_t* p = S + ((long long)(iy + 1) * Ws + ix) * 3; acc[0] += p[0] * w10; acc[1] += p[1] * w10; acc[2] += p[2] * w10; }
+    if (y1 && x1) { const uint8_t* p = S + ((long long)(iy + 1) * Ws + ix + 1) * 3; acc[0] += p[0] * w11; acc[1] += p[1] * w11; acc[2] += p[2] * w11; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int v = (acc[c] + (1 << 14)) >> 15;
+      v = v > 255 ? 255 : v;
+      if (planar) dst[(n * 3 + c) * hw + r] = (uint8_t)v;
+      else dst[i * 3 + c] = (uint8_t)v;
+    }
+  }
+}
+
 }  // namespace s2m2
 
 namespace s2m2 {
@@ -515,6 +552,18 @@ int s2m2b200_image_pad(const void* img, int32_t is_u8, int32_t B, int32_t H, int
 }
 
 }  // extern "C"
+
+int s2m2b200_remap_u8(const uint8_t* src, int64_t src_stride, int32_t Hs, int32_t Ws, const float* mapx, const float* mapy, int32_t N,
+                      int32_t Hd, int32_t Wd, uint8_t* dst, int32_t planar, void* stream) {
+  S2M2_TRACE("remap_u8", src, src_stride, Hs, Ws, mapx, mapy, N, Hd, Wd, dst, planar);
+  S2M2_CHECK(src && mapx && mapy && dst, "remap_u8: null pointer");
+  S2M2_CHECK(Hs > 0 && Ws > 0 && N > 0 && Hd > 0 && Wd > 0 && src_stride >= 0, "remap_u8: bad geometry");
+  const long long n = (long long)N * Hd * Wd, g = (n + 255) / 256;
+  launch_k(remap_u8_kernel, (int)(g > 148 * 32 ? 148 * 32 : g), 256, 0, (cudaStream_t)stream, src, (long long)src_stride, Hs, Ws, mapx, mapy, n, Hd, Wd,
+           dst, planar);
+  S2M2_LAUNCH_OK("remap_u8");
+  return 0;
+}
 
 int s2m2b200_confidence_score(const float* conf, int32_t B, int32_t H, int32_t W, int32_t crop_h, int32_t crop_w, int32_t margin,
                               float* out, void* stream) {

@@ -21,7 +21,7 @@ class HostForward:
     state dict (s2m2.py:69-78 keys); calling the object runs the forward on the current CUDA stream."""
 
     def __init__(self, feature_channels: int, num_transformer: int = 1, use_positivity: bool = False, output_upsample: bool = False,
-                 refine_iter: int = 3, precision: str = "fp16"):
+                 refine_iter: int = 3, precision: str = "fp16", graph: bool = False):
         self.lib = load_library()
         lib = self.lib
         lib.s2m2b200_workspace_bytes.restype = C.c_int64
@@ -32,6 +32,10 @@ class HostForward:
         rc = lib.s2m2b200_create(int(feature_channels), int(num_transformer), int(bool(use_positivity)), int(self.output_upsample), int(refine_iter),
                                  F16 if precision == "fp16" else F32, C.byref(self._h))
         self._chk(rc, "create")
+        if graph:      # the C side captures each shape's launches once per set of buffer addresses and replays
+            self._chk(lib.s2m2b200_set_graph_mode(self._h, 1), "set_graph_mode")
+        self.graph = bool(graph)
+        self._io = {}
         self._work = None
         self._planned = {}
 
@@ -89,9 +93,19 @@ class HostForward:
                 self._work = torch.empty(need, dtype=torch.uint8, device=in0.device)
             sc = 2 if self.output_upsample else 1
             ho, wo = (ch, cw) if ch else (sc * H, sc * W)
-            out = torch.empty((3, B, 1, ho, wo), dtype=torch.float32, device=in0.device)
+            if self.graph:     # stable addresses for the captured graph: private input / output buffers per shape
+                if key not in self._io:
+                    self._io[key] = (torch.empty_like(in0), torch.empty_like(in1),
+                                     torch.empty((3, B, 1, ho, wo), dtype=torch.float32, device=in0.device))
+                g0, g1, out = self._io[key]
+                g0.copy_(in0); g1.copy_(in1)
+                in0, in1 = g0, g1
+            else:
+                out = torch.empty((3, B, 1, ho, wo), dtype=torch.float32, device=in0.device)
             rc = self.lib.s2m2b200_forward(self._h, C.c_void_p(in0.data_ptr()), C.c_void_p(in1.data_ptr()), int(u8), B, H, W, ch, cw,
                                            C.c_void_p(out.data_ptr()), C.c_void_p(self._work.data_ptr()), C.c_int64(self._work.numel()),
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
         self._chk(rc, "forward")
+        if self.graph:
+            out = out.clone()          # the graph's output buffer is overwritten by the next call
         return out[0], out[1], out[2]

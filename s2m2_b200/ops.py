@@ -61,12 +61,12 @@ EXPORTS = [
     "s2m2b200_avgpool2", "s2m2b200_upsample2x", "s2m2b200_gate_blend", "s2m2b200_copy_channels", "s2m2b200_unary",
     "s2m2b200_mul", "s2m2b200_gru_update", "s2m2b200_preprocess", "s2m2b200_stem", "s2m2b200_mask1x_inputs", "s2m2b200_sinkhorn_softargmax", "s2m2b200_cv_lookup",
     "s2m2b200_global_refiner_prep", "s2m2b200_global_refiner_merge", "s2m2b200_local_refiner_prep",
-    "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_filter1x_crop", "s2m2b200_image_pad", "s2m2b200_last_error",
+    "s2m2b200_local_refiner_update", "s2m2b200_upsample4x_convex", "s2m2b200_filter1x", "s2m2b200_filter1x_crop", "s2m2b200_image_pad", "s2m2b200_remap_u8", "s2m2b200_last_error",
     "s2m2b200_preprocess_u8", "s2m2b200_stem_u8", "s2m2b200_confidence_score", "s2m2b200_disparity_to_points",
     "s2m2b200_version", "s2m2b200_launch_count", "s2m2b200_set_plan_mode",
     "s2m2b200_trace_begin", "s2m2b200_trace_note", "s2m2b200_trace_end",
     # the whole forward behind one handle (host side in C++; bound in s2m2_b200/host.py)
-    "s2m2b200_create", "s2m2b200_set_param", "s2m2b200_finalize_params", "s2m2b200_workspace_bytes", "s2m2b200_forward", "s2m2b200_destroy",
+    "s2m2b200_create", "s2m2b200_set_param", "s2m2b200_finalize_params", "s2m2b200_workspace_bytes", "s2m2b200_forward", "s2m2b200_destroy", "s2m2b200_set_graph_mode",
     "s2m2b200_packed_count", "s2m2b200_packed_entry",
 ]
 
@@ -435,6 +435,16 @@ class CudaOps:
         work = torch.empty((B * 3 * (H // factor) * (W // factor),), dtype=torch.float32, device=img.device)
         self._chk(self.lib.s2m2b200_image_pad(C.c_void_p(img.data_ptr()), 1 if img.dtype == torch.uint8 else 0, B, H, W, int(factor),
                                               C.c_void_p(out.data_ptr()), C.c_void_p(work.data_ptr()), self._stream()), "image_pad")
+
+    def remap_u8(self, src, mapx, mapy, out, planar=True):
+        """cv2.remap(uint8 HWC image, INTER_LINEAR, border 0) on the device, bit-exact (image_utils.py:108-136).  src: (Hs,Ws,3) shared
+        by all N maps, or (N,Hs,Ws,3); mapx / mapy: (N,Hd,Wd) fp32; out: (N,3,Hd,Wd) planar or (N,Hd,Wd,3) uint8."""
+        N, Hd, Wd = mapx.shape
+        Hs, Ws = src.shape[-3], src.shape[-2]
+        stride = Hs * Ws * 3 if src.dim() == 4 else 0
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._chk(self.lib.s2m2b200_remap_u8(p(src), C.c_int64(stride), Hs, Ws, p(mapx), p(mapy), N, Hd, Wd, p(out), int(planar), self._stream()),
+                  "remap_u8")
 
     # -- consumers of the output maps (SURVEY §8(f) rows 2, 3)
     def confidence_score(self, conf, crop_hw, margin, out):

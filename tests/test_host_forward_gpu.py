@@ -148,6 +148,23 @@ def test_plain_c_host_program_matches_the_module(tmp_path):
         assert torch.equal(out[i], ref[i].cpu()), name
 
 
+def test_handle_graph_mode_replays_bit_identically():
+    """s2m2b200_set_graph_mode: the C side captures a shape's launches once per set of buffer addresses and replays them."""
+    Cc, NTR, B, H, W = 128, 1, 2, 480, 640
+    sd = random_state_dict(Cc, NTR, seed=3)
+    h = HostForward(Cc, NTR, use_positivity=True).load_state_dict(sd)
+    hg = HostForward(Cc, NTR, use_positivity=True, graph=True).load_state_dict(sd)
+    for seed in (7, 8, 9):                               # first call captures, the next two replay with new inputs
+        left, right = [t.to(DEV) for t in synthetic_pair(B, H, W, seed)]
+        n0 = hg.lib.s2m2b200_launch_count()
+        out = hg(left, right)
+        launched = hg.lib.s2m2b200_launch_count() - n0
+        ref = h(left, right)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(out, ref)), seed
+        assert (launched > 100) == (seed == 7)           # replays enqueue one graph, not the kernels
+
+
 def test_planning_launches_nothing():
     sd = random_state_dict(128, 1, seed=3)
     h = HostForward(128, 1, use_positivity=True).load_state_dict(sd)

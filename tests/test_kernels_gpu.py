@@ -599,3 +599,62 @@ def test_conv_epilogue_modes(ops, emode, kh, kw, cin, cout, act):
     torch.cuda.synchronize()
     _close(out, ref, 6e-3, 6e-3, f"conv epilogue mode {emode} {kh}x{kw} {cin}->{cout}")
     assert torch.equal(r2b[..., cout:], guard)
+
+
+def test_remap_u8_bit_exact_with_opencv():
+    """s2m2b200_remap_u8 (rectify_images on the device, image_utils.py:108-136) against cv2.remap's own outputs
+    (tests/golden/remap_u8.npz, oracle/make_golden_remap.py): real rectification maps of two candidate rotations and a synthetic
+    map with borders / integer coordinates / rounding ties — bit-exact, planar and interleaved, shared and per-candidate sources."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from s2m2_b200 import pre
+    z = np.load(os.path.join(GOLDEN, "remap_u8.npz"))
+    dev = torch.device("cuda", 0)
+    left, right = torch.from_numpy(z["left"]).to(dev), torch.from_numpy(z["right"]).to(dev)
+    cands = [{"leftMapX": z[f"c{i}_lx"], "leftMapY": z[f"c{i}_ly"], "rightMapX": z[f"c{i}_rx"], "rightMapY": z[f"c{i}_ry"]} for i in range(2)]
+    l, r = pre.rectify_images(left, right, cands)                 # (2,3,H,W) planar: the forward's uint8 ingest layout
+    li, ri = pre.rectify_images(left, right, cands, planar=False)
+    for i in range(2):
+        assert np.array_equal(l[i].permute(1, 2, 0).cpu().numpy(), z[f"c{i}_left"])
+        assert np.array_equal(r[i].permute(1, 2, 0).cpu().numpy(), z[f"c{i}_right"])
+        assert np.array_equal(li[i].cpu().numpy(), z[f"c{i}_left"]) and np.array_equal(ri[i].cpu().numpy(), z[f"c{i}_right"])
+    one = pre.rectify_images(left, right, cands[1])[0]
+    assert torch.equal(one[0], l[1])
+    # synthetic map into a destination of another size; per-candidate sources through the op itself
+    from s2m2_b200.ops import CudaOps
+    ops = CudaOps()
+    mx, my = torch.from_numpy(z["syn_mx"]).to(dev)[None], torch.from_numpy(z["syn_my"]).to(dev)[None]
+    out = torch.empty((1,) + tuple(z["syn_out"].shape), dtype=torch.uint8, device=dev)
+    ops.remap_u8(left, mx, my, out, planar=False)
+    assert np.array_equal(out[0].cpu().numpy(), z["syn_out"])
+    src2 = torch.stack([left, right])
+    out2 = torch.empty((2,) + tuple(z["syn_out"].shape), dtype=torch.uint8, device=dev)
+    ops.remap_u8(src2, mx.expand(2, -1, -1).contiguous(), my.expand(2, -1, -1).contiguous(), out2, planar=False)
+    assert np.array_equal(out2[0].cpu().numpy(), z["syn_out"])
+    from oracle.post_oracle import remap_u8
+    assert np.array_equal(out2[1].cpu().numpy(), remap_u8(z["right"], z["syn_mx"], z["syn_my"]))
+
+
+def test_candidate_scores_equal_one_by_one_evaluation():
+    """pre.candidate_scores (N candidate rectifications -> N confidence scores, the calibration optimisers' inner loop,
+    calibration/base.py:15-36, cem.py:64-72) equals rectifying and scoring each candidate on its own."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from s2m2_b200 import pre
+    from s2m2_b200.model import S2M2
+    from s2m2_b200.weights import random_state_dict
+    z = np.load(os.path.join(GOLDEN, "remap_u8.npz"))
+    dev = torch.device("cuda", 0)
+    left, right = torch.from_numpy(z["left"]).to(dev), torch.from_numpy(z["right"]).to(dev)
+    cands = [{"leftMapX": z[f"c{i}_lx"], "leftMapY": z[f"c{i}_ly"], "rightMapX": z[f"c{i}_rx"], "rightMapY": z[f"c{i}_ry"]} for i in range(2)]
+    m = S2M2(32, 1, 1, use_positivity=True).eval()
+    m.load_state_dict(random_state_dict(32, 1, 0))
+    m = m.to(dev)
+    scores = pre.candidate_scores(m, left, right, cands * 3, margin=20, chunk=4)
+    assert scores.shape == (6,) and torch.isfinite(scores).all()
+    for i in range(2):
+        l, r = pre.rectify_images(left, right, cands[i])
+        s = pre.stereo_match(m, l, r, margin=20)[3]
+        assert torch.allclose(scores[i], s[0], atol=1e-6) and torch.allclose(scores[i + 2], s[0], atol=1e-6)

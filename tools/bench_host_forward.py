@@ -63,6 +63,7 @@ def main():
     m.load_state_dict(sd)
     m = m.to(dev)
     h = HostForward(C, NTR, use_positivity=True, refine_iter=3, precision="fp16").load_state_dict(sd)
+    hg = HostForward(C, NTR, use_positivity=True, refine_iter=3, precision="fp16", graph=True).load_state_dict(sd)
     rows = []
     for B in [int(b) for b in a.batches.split(",")]:
         left, right = [t.to(dev) for t in synthetic_pair(B, a.height, a.width, 1)]
@@ -71,6 +72,7 @@ def main():
             m.auto_graph = False
             row["python_schedule_eager"] = dict(zip(KEYS, timed(lambda: m(left, right), a.steps)))
             row["cxx_schedule_eager"] = dict(zip(KEYS, timed(lambda: h(left, right), a.steps)))
+            row["cxx_schedule_graph_mode"] = dict(zip(KEYS, timed(lambda: hg(left, right), a.steps)))
             m.auto_graph = True
             m._graphs = {}
             row["module_graph_replay"] = dict(zip(KEYS, timed(lambda: m(left, right), a.steps)))
