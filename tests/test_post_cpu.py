@@ -138,12 +138,13 @@ def test_points_oracle_against_the_reference_get_pointcloud():
             return "cloud"
     o3d.geometry = types.SimpleNamespace(Image=Image, RGBDImage=RGBDImage, PointCloud=PointCloud)
     o3d.camera = types.SimpleNamespace(PinholeCameraIntrinsic=PinholeCameraIntrinsic)
-    saved = {k: sys.modules.get(k) for k in ("open3d", "s2m2.core.utils.model_utils")}
-    sys.modules["open3d"] = o3d
-    sys.modules.pop("s2m2.core.utils.model_utils", None)
+    saved = {k: sys.modules.get(k) for k in ("open3d",)}
+    sys.modules.setdefault("open3d", o3d)             # only needed for the module's own `import open3d as o3d`
     sys.path.insert(0, "/root/reference/src")
+    MU = old_o3d = None
     try:
         from s2m2.core.utils import model_utils as MU
+        old_o3d, MU.o3d = MU.o3d, o3d                 # the recorder, whatever an earlier test left in sys.modules
         rng = np.random.default_rng(3)
         H, W = 40, 56
         disp = rng.uniform(-2, 60, (H, W)).astype(np.float32)
@@ -152,6 +153,8 @@ def test_points_oracle_against_the_reference_get_pointcloud():
         calib = {"cam0": np.array([[1733.74, 0, 792.27], [0, 1733.74, 541.89], [0, 0, 1]]), "baseline": 536.62, "doffs": 0.0}
         assert MU.get_pointcloud(rgb, disp.copy(), calib, depth_trunc=50.0) == "cloud"
     finally:
+        if MU is not None and old_o3d is not None:
+            MU.o3d = old_o3d
         sys.path.remove("/root/reference/src")
         for k, v in saved.items():
             if v is None:
