@@ -938,7 +938,8 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
   // =2: every BN = 256 layer.
   static const int pair_env = getenv("S2M2_TC_PAIR") ? atoi(getenv("S2M2_TC_PAIR")) : 1;
   const long long nkb_host = (long long)p.taps * (p.cpb1 + p.cpb2);
-  const bool pair = pair_env && !use_v1 && BN == 256 && mtiles * cdiv(a->Cout, BN) >= 296 && (nkb_host >= 16 || pair_env == 2);
+  static const int pair_min_kb = getenv("S2M2_TC_PAIR_MIN_KB") ? atoi(getenv("S2M2_TC_PAIR_MIN_KB")) : 16;   // 64-channel k-blocks
+  const bool pair = pair_env && !use_v1 && BN == 256 && mtiles * cdiv(a->Cout, BN) >= 296 && (nkb_host >= pair_min_kb || pair_env == 2);
   {
     const long long K = (long long)p.taps * (x.C + (x2.ptr ? x2.C : 0));
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Cout}, strides[1] = {(cuuint64_t)K * 2};
