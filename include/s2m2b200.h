@@ -269,6 +269,14 @@ int64_t s2m2b200_workspace_bytes(S2m2Model* m, int32_t B, int32_t H, int32_t W, 
 int s2m2b200_forward(S2m2Model* m, const void* left, const void* right, int32_t in_u8, int32_t B, int32_t H, int32_t W, int32_t crop_h,
                      int32_t crop_w, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 int s2m2b200_set_graph_mode(S2m2Model* m, int32_t on);
+/* run_stereo_matching (model_utils.py:50-95) behind the handle: image_pad of both images to multiples of 32 (image_utils.py:27-63),
+ * the forward, image_crop back to H0 x W0 fused into its last kernel (model_utils.py:88-91) and the interior confidence mean
+ * (model_utils.py:93-94).  left / right: DEVICE (B,3,H0,W0) planar, fp32 or uint8, ANY size >= 32; out: DEVICE 3 x (B,1,H0,W0) fp32
+ * [disparity | occlusion | confidence]; score: DEVICE (B) fp32 or NULL (NaN when 2*margin leaves no interior); the reference uses
+ * margin = 100.  Workspace from s2m2b200_stereo_match_workspace_bytes. */
+int64_t s2m2b200_stereo_match_workspace_bytes(S2m2Model* m, int32_t B, int32_t H0, int32_t W0);
+int s2m2b200_stereo_match(S2m2Model* m, const void* left, const void* right, int32_t in_u8, int32_t B, int32_t H0, int32_t W0, int32_t margin,
+                          float* out, float* score, void* workspace, int64_t workspace_bytes, void* stream);
 void s2m2b200_destroy(S2m2Model* m);
 /* The packed blob's directory (tests): entry `index` of s2m2b200_packed_count; ptr is device memory when *on_device. */
 int64_t s2m2b200_packed_count(const S2m2Model* m);

@@ -1313,4 +1313,63 @@ int s2m2b200_forward(S2m2Model* m, const void* left, const void* right, int32_t 
   S2M2_GUARD_END(-1)
 }
 
+// ---- run_stereo_matching (model_utils.py:50-95) behind the handle: image_pad -> forward -> image_crop -> interior confidence mean ----
+namespace {
+struct MatchLayout {
+  int Hn, Wn;
+  size_t lp, rp, padwork, fwd, total;
+};
+MatchLayout match_layout(int B, int H0, int W0, size_t fwd_bytes) {
+  MatchLayout l;
+  l.Hn = (H0 + 31) / 32 * 32;
+  l.Wn = (W0 + 31) / 32 * 32;
+  const size_t img = align_up((size_t)B * 3 * l.Hn * l.Wn * 4, 256);
+  l.lp = 0;
+  l.rp = img;
+  l.padwork = 2 * img;
+  l.fwd = l.padwork + align_up((size_t)B * 3 * (H0 / 32) * (W0 / 32) * 4 + 4, 256);
+  l.total = l.fwd + fwd_bytes;
+  return l;
+}
+}  // namespace
+
+int64_t s2m2b200_stereo_match_workspace_bytes(S2m2Model* m, int32_t B, int32_t H0, int32_t W0) {
+  S2M2_CHECK(m && m->finalized, "stereo_match_workspace_bytes: model not finalized");
+  S2M2_CHECK(B > 0 && H0 >= 32 && W0 >= 32, "stereo_match_workspace_bytes: images must be at least 32 x 32");
+  S2M2_CHECK(!m->output_upsample, "stereo_match: not defined for output_upsample models (image_crop would cut the 2x maps)");
+  const int Hn = (H0 + 31) / 32 * 32, Wn = (W0 + 31) / 32 * 32;
+  const int64_t fwd = s2m2b200_workspace_bytes(m, B, Hn, Wn, 0, H0, W0);
+  if (fwd < 0) return fwd;
+  return (int64_t)match_layout(B, H0, W0, (size_t)fwd).total;
+}
+
+int s2m2b200_stereo_match(S2m2Model* m, const void* left, const void* right, int32_t in_u8, int32_t B, int32_t H0, int32_t W0, int32_t margin,
+                          float* out, float* score, void* workspace, int64_t workspace_bytes, void* stream) {
+  S2M2_CHECK(m && m->finalized && left && right && out && workspace, "stereo_match: null argument / model not finalized");
+  S2M2_CHECK(B > 0 && H0 >= 32 && W0 >= 32, "stereo_match: images must be at least 32 x 32");
+  S2M2_CHECK(!m->output_upsample, "stereo_match: not defined for output_upsample models");
+  S2M2_CHECK(((uintptr_t)workspace & 255) == 0, "stereo_match: the workspace must be 256-byte aligned");
+  const int Hn = (H0 + 31) / 32 * 32, Wn = (W0 + 31) / 32 * 32;
+  const int64_t fwd = s2m2b200_workspace_bytes(m, B, Hn, Wn, 0, H0, W0);
+  if (fwd < 0) return -1;
+  const MatchLayout l = match_layout(B, H0, W0, (size_t)fwd);
+  S2M2_CHECK((size_t)workspace_bytes >= l.total, "stereo_match: workspace of %lld bytes, %zu needed (s2m2b200_stereo_match_workspace_bytes)",
+             (long long)workspace_bytes, l.total);
+  char* w = (char*)workspace;
+  float *lp = (float*)(w + l.lp), *rp = (float*)(w + l.rp), *pw = (float*)(w + l.padwork);
+  // model_utils.py:72-73: both images padded to multiples of 32 with the blurred fill (image_utils.py:27-63)
+  if (s2m2b200_image_pad(left, in_u8, B, H0, W0, 32, lp, pw, stream) != 0) return -1;
+  if (s2m2b200_image_pad(right, in_u8, B, H0, W0, 32, rp, pw, stream) != 0) return -1;
+  // the forward; its last kernel writes only the centre H0 x W0 window = image_crop (model_utils.py:88-91)
+  if (s2m2b200_forward(m, lp, rp, 0, B, Hn, Wn, H0, W0, out, w + l.fwd, fwd, stream) != 0) return -1;
+  if (score) {   // model_utils.py:93-94: mean of the cropped confidence map without a `margin`-wide frame
+    if (margin > 0 && H0 > 2 * margin && W0 > 2 * margin) {
+      if (s2m2b200_confidence_score(out + (size_t)2 * B * H0 * W0, B, H0, W0, H0, W0, margin, score, stream) != 0) return -1;
+    } else {
+      S2M2_CHECK(cudaMemsetAsync(score, 0xFF, (size_t)B * 4, (cudaStream_t)stream) == cudaSuccess, "stereo_match: memset failed");   // NaN: no interior
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

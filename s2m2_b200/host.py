@@ -25,6 +25,7 @@ class HostForward:
         self.lib = load_library()
         lib = self.lib
         lib.s2m2b200_workspace_bytes.restype = C.c_int64
+        lib.s2m2b200_stereo_match_workspace_bytes.restype = C.c_int64
         lib.s2m2b200_packed_count.restype = C.c_int64
         lib.s2m2b200_destroy.restype = None
         self.output_upsample = bool(output_upsample)
@@ -109,3 +110,26 @@ class HostForward:
         if self.graph:
             out = out.clone()          # the graph's output buffer is overwritten by the next call
         return out[0], out[1], out[2]
+
+    @torch.no_grad()
+    def stereo_match(self, left: torch.Tensor, right: torch.Tensor, margin: int = 100):
+        """``run_stereo_matching`` (model_utils.py:50-95) through ``s2m2b200_stereo_match``: (B,3,H0,W0) uint8 / fp32 CUDA images of
+        any size >= 32 -> disparity, occlusion, confidence as (B,H0,W0) maps and the (B,) confidence scores, all on the device."""
+        if left.shape != right.shape or left.dim() != 4 or left.shape[1] != 3 or not left.is_cuda:
+            raise ValueError("expected two CUDA (B,3,H,W) images of equal shape")
+        u8 = left.dtype == torch.uint8 and right.dtype == torch.uint8
+        in0, in1 = (left.contiguous(), right.contiguous()) if u8 else (left.float().contiguous(), right.float().contiguous())
+        B, _, H0, W0 = in0.shape
+        with torch.cuda.device(in0.device):
+            need = int(self.lib.s2m2b200_stereo_match_workspace_bytes(self._h, B, H0, W0))
+            if need < 0:
+                self._chk(-1, "stereo_match_workspace_bytes")
+            if self._work is None or self._work.numel() < need or self._work.device != in0.device:
+                self._work = torch.empty(need, dtype=torch.uint8, device=in0.device)
+            out = torch.empty((3, B, H0, W0), dtype=torch.float32, device=in0.device)
+            score = torch.empty((B,), dtype=torch.float32, device=in0.device)
+            rc = self.lib.s2m2b200_stereo_match(self._h, C.c_void_p(in0.data_ptr()), C.c_void_p(in1.data_ptr()), int(u8), B, H0, W0, int(margin),
+                                                C.c_void_p(out.data_ptr()), C.c_void_p(score.data_ptr()), C.c_void_p(self._work.data_ptr()),
+                                                C.c_int64(self._work.numel()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._chk(rc, "stereo_match")
+        return out[0], out[1], out[2], score

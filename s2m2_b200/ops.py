@@ -66,7 +66,7 @@ EXPORTS = [
     "s2m2b200_version", "s2m2b200_launch_count", "s2m2b200_set_plan_mode",
     "s2m2b200_trace_begin", "s2m2b200_trace_note", "s2m2b200_trace_end",
     # the whole forward behind one handle (host side in C++; bound in s2m2_b200/host.py)
-    "s2m2b200_create", "s2m2b200_set_param", "s2m2b200_finalize_params", "s2m2b200_workspace_bytes", "s2m2b200_forward", "s2m2b200_destroy", "s2m2b200_set_graph_mode",
+    "s2m2b200_create", "s2m2b200_set_param", "s2m2b200_finalize_params", "s2m2b200_workspace_bytes", "s2m2b200_forward", "s2m2b200_destroy", "s2m2b200_set_graph_mode", "s2m2b200_stereo_match", "s2m2b200_stereo_match_workspace_bytes",
     "s2m2b200_packed_count", "s2m2b200_packed_entry",
 ]
 

@@ -165,6 +165,28 @@ def test_handle_graph_mode_replays_bit_identically():
         assert (launched > 100) == (seed == 7)           # replays enqueue one graph, not the kernels
 
 
+@pytest.mark.parametrize("H0,W0,u8", [(300, 410, True), (256, 320, False)])
+def test_handle_stereo_match_equals_the_python_chain(H0, W0, u8):
+    """s2m2b200_stereo_match (pad -> forward -> fused crop -> confidence mean in C++) against pre.stereo_match over the module."""
+    from s2m2_b200 import pre
+    Cc, NTR, B = 64, 1, 2
+    sd = random_state_dict(Cc, NTR, seed=3)
+    m, h = _pair(Cc, NTR, "fp16", sd, use_positivity=True)
+    left, right = synthetic_pair(B, H0, W0, 5)
+    if u8:
+        left, right = left.to(torch.uint8), right.to(torch.uint8)
+    left, right = left.to(DEV), right.to(DEV)
+    ref = pre.stereo_match(m, left, right, margin=100)
+    out = h.stereo_match(left, right, margin=100)
+    torch.cuda.synchronize()
+    for name, a, b in zip(("disparity", "occlusion", "confidence", "score"), out, ref):
+        assert a.shape == b.shape, name
+        assert torch.equal(a, b), f"{name}: {(a - b).abs().max().item():.3e}"
+    assert torch.isfinite(out[3]).all()
+    small = h.stereo_match(left[..., :96, :128].contiguous(), right[..., :96, :128].contiguous(), margin=100)
+    assert torch.isnan(small[3]).all() and torch.isfinite(small[0]).all()      # no interior left by the margin: NaN, like the Python chain
+
+
 def test_planning_launches_nothing():
     sd = random_state_dict(128, 1, seed=3)
     h = HostForward(128, 1, use_positivity=True).load_state_dict(sd)
