@@ -283,41 +283,69 @@ __global__ void __launch_bounds__(256) conv_smallk_kernel(ConvP p) {
   __syncthreads();
   const int NG = p.Cout >> 3;                    // threads per pixel
   const long long total = (long long)p.M * NG;
+  if constexpr (VEC) {
+    // the hot variant (the refiner's 1 / 2 / 9-channel feature layers, 12 launches per forward): the channel group of a thread is
+    // fixed (blockDim is a multiple of NG), pixels advance by a constant stride, taps come from a table of element offsets — no
+    // 64-bit division and no per-tap address arithmetic in the loop; GELU through the 10-instruction gelu_fast of the tcgen05 epilogues
+    int* soff = stab + p.K;                      // per k: element offset (dy * W + dx) * x_ld + ci relative to the centre pixel
+    for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+      const int e = stab[k];
+      soff[k] = (((e >> 16) - 128) * p.W + (((e >> 8) & 255) - 128)) * (int)p.x_ld + (e & 255);
+    }
+    __syncthreads();
+    const int g = threadIdx.x % NG, cb = 8 * g;
+    const int ppb = blockDim.x / NG;             // pixels per block and iteration
+    const long long mstep = (long long)gridDim.x * ppb;
+    float4 b0 = *(const float4*)(sb + cb), b1 = *(const float4*)(sb + cb + 4);
+    for (long long m = (long long)blockIdx.x * ppb + threadIdx.x / NG; m < p.M; m += mstep) {
+      const int mi = (int)m;                     // M < 2^31 (checked by the launcher)
+      const int ox = mi % p.Wo, t = mi / p.Wo;
+      const int oy = t % p.Ho, n = t / p.Ho;
+      const int cy = oy * p.stride, cx = ox * p.stride;
+      const long long base = (((long long)n * p.H + cy) * p.W + cx) * p.x_ld;
+      float o[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int k = 0; k < p.K; ++k) {
+        const int e = stab[k];
+        const int iy = cy + (e >> 16) - 128, ix = cx + ((e >> 8) & 255) - 128;
+        float a = 0.f;
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) a = ld1(p.x, base + soff[k], p.xh);
+        const float4 w0 = *(const float4*)(sw + k * p.Cout + cb), w1 = *(const float4*)(sw + k * p.Cout + cb + 4);
+        o[0] = fmaf(a, w0.x, o[0]); o[1] = fmaf(a, w0.y, o[1]); o[2] = fmaf(a, w0.z, o[2]); o[3] = fmaf(a, w0.w, o[3]);
+        o[4] = fmaf(a, w1.x, o[4]); o[5] = fmaf(a, w1.y, o[5]); o[6] = fmaf(a, w1.z, o[6]); o[7] = fmaf(a, w1.w, o[7]);
+      }
+      __half2 h[4];
+      if (p.act == S2M2_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(gelu_fast(o[2 * j]), gelu_fast(o[2 * j + 1]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(act_apply_fast(o[2 * j], p.act), act_apply_fast(o[2 * j + 1], p.act));
+      }
+      *(uint4*)((__half*)p.y + m * p.y_ld + cb) = *(uint4*)h;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / NG), g = (int)(i - (long long)m * NG);
     const int ox = m % p.Wo;
     const int t = m / p.Wo;
     const int oy = t % p.Ho, n = t / p.Ho;
-    const int cb = VEC ? 8 * g : g, cs = VEC ? 1 : NG;     // first channel and channel step of this thread
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = sb[cb + j * cs];
+    for (int j = 0; j < 8; ++j) o[j] = sb[g + j * NG];
     const long long img = (long long)n * p.H;
     for (int k = 0; k < p.K; ++k) {
       const int e = stab[k];
       const int iy = oy * p.stride + (e >> 16) - 128, ix = ox * p.stride + ((e >> 8) & 255) - 128;
       float a = 0.f;
       if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) a = ld1(p.x, ((img + iy) * p.W + ix) * p.x_ld + (e & 255), p.xh);
-      if constexpr (VEC) {
-        const float4 w0 = *(const float4*)(sw + k * p.Cout + cb), w1 = *(const float4*)(sw + k * p.Cout + cb + 4);
-        o[0] = fmaf(a, w0.x, o[0]); o[1] = fmaf(a, w0.y, o[1]); o[2] = fmaf(a, w0.z, o[2]); o[3] = fmaf(a, w0.w, o[3]);
-        o[4] = fmaf(a, w1.x, o[4]); o[5] = fmaf(a, w1.y, o[5]); o[6] = fmaf(a, w1.z, o[6]); o[7] = fmaf(a, w1.w, o[7]);
-      } else {
-        const float* wr = sw + k * p.Cout + g;
+      const float* wr = sw + k * p.Cout + g;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(a, wr[j * NG], o[j]);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(a, wr[j * NG], o[j]);
     }
-    if constexpr (VEC) {
-      __half2 h[4];
+    const long long off = (long long)m * p.y_ld + g;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(act_apply_fast(o[2 * j], p.act), act_apply_fast(o[2 * j + 1], p.act));
-      *(uint4*)((__half*)p.y + (long long)m * p.y_ld + cb) = *(uint4*)h;
-    } else {
-      const long long off = (long long)m * p.y_ld + g;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) st1(p.y, off + j * NG, p.yh, act_apply(o[j], p.act));
-    }
+    for (int j = 0; j < 8; ++j) st1(p.y, off + j * NG, p.yh, act_apply(o[j], p.act));
   }
 }
 
@@ -358,8 +386,10 @@ int conv_simt_launch(const S2m2Conv* a, cudaStream_t s) {
     const long long total = (long long)p.M * (p.Cout / 8);
     long long g = (total + 255) / 256;
     if (g > 148LL * 32) g = 148LL * 32;
-    const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout + p.K);
-    const bool v8 = p.yh && p.y_ld % 8 == 0 && aligned(y.ptr, 16) && p.Cin < 256 && p.KH <= 128 && p.KW <= 128;
+    const size_t smem = sizeof(float) * (size_t)(p.Cout * p.K + p.Cout + 2 * p.K);
+    // (the vector variant: fixed channel group per thread -> 256 % (Cout / 8) == 0; 32-bit tap offsets and pixel indices)
+    const bool v8 = p.yh && p.y_ld % 8 == 0 && aligned(y.ptr, 16) && p.Cin < 256 && p.KH <= 128 && p.KW <= 128 && 256 % (p.Cout / 8) == 0 &&
+                    p.Cout % 8 == 0 && (long long)x.N * p.H * p.W * p.x_ld < (1LL << 31) && p.M < (1LL << 31) && (long long)(p.KH + 1) * p.W * p.x_ld < (1LL << 30);
     if (v8) launch_k(conv_smallk_kernel<true>, (int)g, 256, smem, s, p);
     else launch_k(conv_smallk_kernel<false>, (int)g, 256, smem, s, p);
     S2M2_LAUNCH_OK("conv_smallk");

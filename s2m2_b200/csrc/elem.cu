@@ -207,29 +207,53 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return v;
 }
 
+// Bilinear x2 (align_corners = False: weights .75 / .25, clamped at the border).  One thread turns a 2x2 block of input pixels
+// (columns i-1, i and rows j-1, j, clamped) into the 2x2 block of output pixels (2i-1, 2i) x (2j-1, 2j) that depends on exactly those
+// four: 4 loads + 4 unpacks per FOUR outputs (the one-output-per-thread version spent its time unpacking: 29 % of the HBM peak).
 __global__ void upsample2x_h8_kernel(const __half* __restrict__ x, long long xld, __half* __restrict__ y, long long yld, int N, int H, int W,
                                      int C8, int PPB) {
   pdl_sync();
   const int c8 = threadIdx.x % C8, p0 = threadIdx.x / C8;
-  const int Ho = 2 * H, Wo = 2 * W;
-  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
-    const int n = row / Ho, oy = row - n * Ho;
-    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
-    const float ly = sy - y0, hy = 1.f - ly;
-    const __half* r0 = x + ((long long)n * H + y0) * W * xld + c8 * 8;
-    const __half* r1 = x + ((long long)n * H + y1) * W * xld + c8 * 8;
-    __half* out = y + (long long)row * Wo * yld + c8 * 8;
-    for (int ox = p0; ox < Wo; ox += PPB) {
-      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-      const int x0 = (int)sx, x1 = min(x0 + 1, W - 1);
-      const float lx = sx - x0, hx = 1.f - lx;
-      float a[8], b[8], d[8], e[8], o[8];
-      unpack8(*(const uint4*)(r0 + x0 * xld), a); unpack8(*(const uint4*)(r0 + x1 * xld), b);
-      unpack8(*(const uint4*)(r1 + x0 * xld), d); unpack8(*(const uint4*)(r1 + x1 * xld), e);
+  const int Wo = 2 * W;
+  for (int row = blockIdx.x; row < N * (H + 1); row += gridDim.x) {
+    const int n = row / (H + 1), j = row - n * (H + 1);
+    const int ya = max(j - 1, 0), yb = min(j, H - 1);
+    const __half* r0 = x + ((long long)n * H + ya) * W * xld + c8 * 8;
+    const __half* r1 = x + ((long long)n * H + yb) * W * xld + c8 * 8;
+    __half* o0 = y + ((long long)n * 2 * H + 2 * j - 1) * Wo * yld + c8 * 8;   // output row 2j-1 (exists for j >= 1)
+    __half* o1 = o0 + (long long)Wo * yld;                                      // output row 2j   (exists for j <= H-1)
+    const bool top = j >= 1, bot = j <= H - 1;
+    for (int i = p0; i <= W; i += PPB) {
+      const int xa = max(i - 1, 0), xb = min(i, W - 1);
+      float a[8], b[8], d[8], e[8], t0[8], t1[8], u0[8], u1[8], o[8];
+      unpack8(*(const uint4*)(r0 + xa * xld), a); unpack8(*(const uint4*)(r0 + xb * xld), b);
+      unpack8(*(const uint4*)(r1 + xa * xld), d); unpack8(*(const uint4*)(r1 + xb * xld), e);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * d[k] + lx * e[k]);
-      *(uint4*)(out + ox * yld) = pack8(o);
+      for (int k = 0; k < 8; ++k) {
+        t0[k] = 0.75f * a[k] + 0.25f * b[k]; t1[k] = 0.25f * a[k] + 0.75f * b[k];    // row ya at output columns 2i-1, 2i
+        u0[k] = 0.75f * d[k] + 0.25f * e[k]; u1[k] = 0.25f * d[k] + 0.75f * e[k];    // row yb
+      }
+      const bool lft = i >= 1, rgt = i <= W - 1;
+      if (top && lft) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.75f * t0[k] + 0.25f * u0[k];
+        *(uint4*)(o0 + (long long)(2 * i - 1) * yld) = pack8(o);
+      }
+      if (top && rgt) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.75f * t1[k] + 0.25f * u1[k];
+        *(uint4*)(o0 + (long long)(2 * i) * yld) = pack8(o);
+      }
+      if (bot && lft) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.25f * t0[k] + 0.75f * u0[k];
+        *(uint4*)(o1 + (long long)(2 * i - 1) * yld) = pack8(o);
+      }
+      if (bot && rgt) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.25f * t1[k] + 0.75f * u1[k];
+        *(uint4*)(o1 + (long long)(2 * i) * yld) = pack8(o);
+      }
     }
   }
 }
@@ -622,7 +646,7 @@ int s2m2b200_upsample2x(const S2m2Tensor* x, const S2m2Tensor* y, void* stream) 
   S2M2_CHECK(vec4_ok(*x) && vec4_ok(*y), "upsample2x: needs C,ld multiples of 4 and aligned bases");
   if (h8_ok(*x) && h8_ok(*y)) {
     const int C8 = x->C / 8, PPB = C8 >= 256 ? 1 : 256 / C8;
-    const int rows = y->N * y->H;
+    const int rows = x->N * (x->H + 1);      // one block iteration per pair of output rows (2j-1, 2j), j = 0..H
     launch_k(upsample2x_h8_kernel, rows < 148 * 16 ? rows : 148 * 16, C8 * PPB, 0, (cudaStream_t)stream, (const __half*)x->ptr, x->ld,
              (__half*)y->ptr, y->ld, x->N, x->H, x->W, C8, PPB);
     S2M2_LAUNCH_OK("upsample2x_h8");

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report: the LAST launch of every kernel, one markdown row each.
 
-    python tools/ncu_summary.py gpurun_out/r2/prof_r2c.ncu-rep [> profiles/....md]
+    python tools/ncu_summary.py gpurun_out/r2/prof_r2c.ncu-rep [--ids 3,4,5,18] [> profiles/....md]
+
+--ids: report these launch IDs (in this order) instead of the last launch per kernel name.
 """
 import csv
 import io
@@ -37,8 +39,13 @@ def main():
     hdr, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(hdr)}
     last = {}
-    for r in rows[2:]:
-        last[r[col["Kernel Name"]]] = r            # later launches overwrite the warm-up launch
+    ids = [a.split("=")[1] if "=" in a else sys.argv[i + 1] for i, a in enumerate(sys.argv) if a.startswith("--ids")]
+    if ids:
+        by_id = {r[col["ID"]]: r for r in rows[2:]}
+        last = {f"#{i} {by_id[i][col['Kernel Name']]}": by_id[i] for i in ids[0].split(",")}
+    else:
+        for r in rows[2:]:
+            last[r[col["Kernel Name"]]] = r        # later launches overwrite the warm-up launch
     pick = lambda r, k: to_f(r[col[M[k]]]) if M[k] in col else float("nan")
     scale = lambda k: {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[col[M[k]]].strip(), 1.0) if M[k] in col else 1.0
     bscale = lambda k: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(units[col[M[k]]].strip(), 1.0) if M[k] in col else 1.0
