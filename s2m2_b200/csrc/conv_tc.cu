@@ -339,10 +339,17 @@ constexpr int TC2_THREADS = 64 + 128 * TC2_EPI_GROUPS;   // 576
 // PAIR: two CTAs of a cluster (one TPC) work on two vertically adjacent 128-pixel tiles with the same output channels as ONE
 // 256 x BN tcgen05.mma.cta_group::2: each CTA loads its own A tile but only half of the weight tile, so the L2->SMEM operand
 // traffic per FLOP (the limiter of the 3x3 convolutions) drops by a third and the ring gets deeper.
-template <int BN, int STAGES, bool PAIR>
+// BRES (weights resident): layers whose whole weight matrix is one narrow tile of a few k-blocks (64-wide 3x3 / 1x1 layers at full
+// and half resolution: K <= 576, one n-tile) load it ONCE per CTA into its own shared-memory region instead of streaming it
+// through the ring with every pixel tile — every CTA re-reading the same 8-72 KB from the same few L2 slices was what held these
+// layers at 55 GB/s per SM (profiles/r2_kernels_ncu2.md: the epilogue warps wait for the accumulator, the ring for its loads).
+constexpr int TC2_BRES_MAX_KB = 9;
+template <int BN, int STAGES, bool PAIR, bool BRES = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcP p,
                                                                             int m_tiles, int n_tiles) {
+  static_assert(!(PAIR && BRES), "weights-resident variant is single-CTA");
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;
+  constexpr int B_SLOTS = BRES ? TC2_BRES_MAX_KB : STAGES;
   uint32_t rank = 0;
   if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -350,10 +357,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   constexpr uint32_t STG_BYTES = 32 * (BN / TC2_EPI_GROUPS) * 2;          // per epilogue warp: 32 rows x CG fp16
-  uint8_t* sStage = sB + STAGES * B_BYTES;                                  // 16 warps x STG_BYTES, 1024-aligned
-  uint64_t* bars = (uint64_t*)(sStage + 4 * TC2_EPI_GROUPS * 1024 * ((STG_BYTES + 1023) / 1024));  // full[S], empty[S], tfull[2], tempty[2], rbar[16]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4 + 4 * TC2_EPI_GROUPS);
+  uint8_t* sStage = sB + B_SLOTS * B_BYTES;                                 // 16 warps x STG_BYTES, 1024-aligned
+  uint64_t* bars = (uint64_t*)(sStage + 4 * TC2_EPI_GROUPS * 1024 * ((STG_BYTES + 1023) / 1024));  // full[S], empty[S], tfull[2], tempty[2], rbar[16], bres
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4 + 4 * TC2_EPI_GROUPS + 1);
   const uint32_t rbar0 = smem_u32(bars + 2 * STAGES + 4);
+  const uint32_t bres_bar = smem_u32(bars + 2 * STAGES + 4 + 4 * TC2_EPI_GROUPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
@@ -376,6 +384,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
       mbar_init(tempty0 + 8 * a, 4 * TC2_EPI_GROUPS * (PAIR ? 2 : 1));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int a = 0; a < 4 * TC2_EPI_GROUPS; ++a) mbar_init(rbar0 + 8 * a, 1);
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -426,6 +435,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
         if constexpr (PAIR) tma_load_4d_pair(m, dst, bar, c0, c1, c2, c3);
         else tma_load_4d(m, dst, bar, c0, c1, c2, c3);
       };
+      if constexpr (BRES) {   // the whole weight tile, once (n_tiles == 1: it never changes)
+        if (first_tile < total_tiles) {
+          mbar_expect_tx(bres_bar, (uint32_t)nkb * B_BYTES);
+          for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&maps.w, smem_u32(sB + kb * B_BYTES), bres_bar, kb * TC_BK, 0);
+        }
+      }
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int n0, img, x0, y0;
         tile_coords(tile, n0, img, x0, y0);
@@ -436,11 +451,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           if constexpr (PAIR) {
             if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + B_BYTES));   // leader's barrier counts both CTAs' bytes
           } else {
-            mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+            mbar_expect_tx(full0 + 8 * s, BRES ? A_BYTES : A_BYTES + B_BYTES);
           }
           const int tap = kb / cpb, ch = kb - tap * cpb;
           const int ky = tap / p.KW, kx = tap - ky * p.KW;
-          const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + s * B_BYTES);
+          const uint32_t dstA = smem_u32(sA + s * A_BYTES), dstB = smem_u32(sB + (BRES ? 0 : s) * B_BYTES);
           const int dx = kx - p.pw, dy = ky - p.ph;
           if (p.stride == 1) {
             if (ch < p.cpb1) load_a(&maps.act[0], dstA, full0 + 8 * s, ch * TC_BK, x0 + dx, y0 + dy, img);
@@ -449,7 +464,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
             load_a(&maps.act[(dy & 1) * 2 + (dx & 1)], dstA, full0 + 8 * s, ch * TC_BK, x0 + (dx >> 1), y0 + (dy >> 1), img);
           }
           if constexpr (PAIR) tma_load_2d_pair(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0 + (int)rank * (BN / 2));   // this CTA's half of the weight rows
-          else tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
+          else if constexpr (!BRES) tma_load_2d(&maps.w, dstB, full0 + 8 * s, kb * TC_BK, n0);
         }
       }
     }
@@ -458,6 +473,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
     if (lane == 0 && rank == 0) {   // PAIR: the leader issues for both SMs
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       uint32_t it = 0, lt = 0;  // k-block counter, local tile counter
+      if constexpr (BRES) {
+        if (first_tile < total_tiles) mbar_wait(bres_bar, 0);
+      }
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++lt) {
         const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);          // epilogue has drained this accumulator
@@ -468,7 +486,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_persistent_kernel(cons
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t ad = make_sdesc(smem_u32(sA + s * A_BYTES)), bd = make_sdesc(smem_u32(sB + s * B_BYTES));
+          const uint64_t ad = make_sdesc(smem_u32(sA + s * A_BYTES)), bd = make_sdesc(smem_u32(sB + (BRES ? kb : s) * B_BYTES));
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             if constexpr (PAIR) umma_f16_pair(tacc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
@@ -840,17 +858,18 @@ static int launch_tc(const TcMaps& maps, const TcP& p, dim3 grid, cudaStream_t s
   return 0;
 }
 
-template <int BN, int STAGES, bool PAIR = false>
+template <int BN, int STAGES, bool PAIR = false, bool BRES = false>
 static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles, cudaStream_t s) {
   constexpr size_t stg = 4 * TC2_EPI_GROUPS * 1024 * ((32 * (BN / TC2_EPI_GROUPS) * 2 + 1023) / 1024);
-  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2 + (PAIR ? BN / 2 : BN) * TC_BK * 2) + stg + (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS) * 8 + 16 + 1024;
+  constexpr size_t smem = STAGES * (TC_BM * TC_BK * 2) + (BRES ? TC2_BRES_MAX_KB : STAGES) * ((PAIR ? BN / 2 : BN) * TC_BK * 2) + stg +
+                          (2 * STAGES + 4 + 4 * TC2_EPI_GROUPS + 1) * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr[S2M2_MAX_DEVICES] = {false};
   static int sms_of[S2M2_MAX_DEVICES] = {0};
   const int di = current_device_index();
   int& sms = sms_of[di];
   if (!attr[di]) {
-    cudaError_t e = set_func_attr(conv_tc_persistent_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_func_attr(conv_tc_persistent_kernel<BN, STAGES, PAIR, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     S2M2_CHECK(e == cudaSuccess, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
@@ -872,13 +891,13 @@ static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (!plan_mode()) (void)cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, STAGES, PAIR>, maps, p, m_tiles, n_tiles);
+    if (!plan_mode()) (void)cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, STAGES, PAIR, BRES>, maps, p, m_tiles, n_tiles);
     S2M2_LAUNCH_OK("conv_tc_pair");
     return 0;
   }
   const long long tiles = (long long)m_tiles * n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  launch_k(conv_tc_persistent_kernel<BN, STAGES, PAIR>, grid, TC2_THREADS, smem, s, maps, p, m_tiles, n_tiles);
+  launch_k(conv_tc_persistent_kernel<BN, STAGES, PAIR, BRES>, grid, TC2_THREADS, smem, s, maps, p, m_tiles, n_tiles);
   S2M2_LAUNCH_OK("conv_tc_persistent");
   return 0;
 }
@@ -993,6 +1012,8 @@ int conv_tc_launch(const S2m2Conv* a, cudaStream_t s) {
     if (pair) return launch_tc2<256, 5, true>(maps, p, (int)mtiles, nt, s);
     if (BN == 256) return launch_tc2<256, 3>(maps, p, (int)mtiles, nt, s);
     if (BN == 128) return launch_tc2<128, 5>(maps, p, (int)mtiles, nt, s);
+    static const int bres_env = getenv("S2M2_TC_BRES") ? atoi(getenv("S2M2_TC_BRES")) : 1;   // 0: stream the weights through the ring
+    if (bres_env && nt == 1 && nkb_host <= TC2_BRES_MAX_KB) return launch_tc2<64, 8, false, true>(maps, p, (int)mtiles, nt, s);
     return launch_tc2<64, 8>(maps, p, (int)mtiles, nt, s);
   }
   dim3 grid((unsigned)mtiles, cdiv(a->Cout, BN));
