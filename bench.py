@@ -200,9 +200,13 @@ def main():
     if world > 1:
         import datetime
         import torch.distributed as dist
-        # evidence of the communicator (rank / nranks lines of NCCL's own init log), unless the caller already chose a level
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # evidence of the communicator: NCCL's own init log (the "rank r nranks N ... Init COMPLETE" lines), sent to stderr so that
+        # stdout stays the one JSON line.  A quieter preset (unset / VERSION / WARN) is raised to INFO; INFO / TRACE / a log file
+        # chosen by the caller are left alone.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
 
     model = S2M2(C, 1, NTR, use_positivity=True, refine_iter=3, precision=args.precision).eval()
