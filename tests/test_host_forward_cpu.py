@@ -93,6 +93,8 @@ CASES = [
     (64, 1, "fp16", 1, 96, 160, torch.float32, None, dict(output_upsample=True)),
     (128, 1, "fp16", 2, 480, 640, torch.float32, None, dict(use_positivity=True)),          # S: fused token kernels above their thresholds
     (256, 3, "fp16", 1, 1024, 1216, torch.float32, None, dict(use_positivity=True)),        # L, the benchmarked configuration
+    (192, 2, "fp16", 1, 256, 384, torch.float32, None, dict(use_positivity=True)),          # M: head dims 192 / 96 / 48 / 48
+    (384, 3, "fp16", 1, 512, 640, torch.uint8, (500, 620), dict(use_positivity=True)),      # XL channels: the wide-C kernel variants
 ]
 
 

@@ -38,6 +38,8 @@ CASES = [
     (64, 1, "fp16", 1, 96, 160, False, None, dict(output_upsample=True)),
     (128, 1, "fp16", 2, 480, 640, False, None, dict(use_positivity=True)),
     (256, 3, "fp16", 1, 1024, 1216, False, None, dict(use_positivity=True)),
+    (192, 2, "fp16", 1, 256, 384, False, None, dict(use_positivity=True)),
+    (384, 3, "fp16", 1, 512, 640, True, (500, 620), dict(use_positivity=True)),
 ]
 
 
