@@ -26,13 +26,27 @@ bool plan_without_device() {
   return have == 0;
 }
 
-bool pdl_enabled() {   // S2M2_PDL=1 turns programmatic dependent launch on.  Default off: inside the captured CUDA graph the
-  static int on = -1;  // kernel-to-kernel gaps are already hidden and the measured forward time did not improve (34.1 vs 34.3 ms).
-  if (on < 0) {
+int pdl_mode() {   // S2M2_PDL: 0 = never, 1 = always, unset / 2 = auto: on for launches into a stream that is not being captured
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("S2M2_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
-  return on != 0;
+  return mode;
+}
+// Programmatic dependent launch: every kernel runs pdl_sync() before it touches global memory, so with the attribute its CTAs are
+// scheduled (and run their shared-memory / TMEM / barrier prologue) while the previous kernel drains.  Eager launches gain from it
+// (the ~880 launches of a single-pair forward: 32.0 -> 31.1 ms against 30.6 ms for the graph replay); inside a captured CUDA graph the
+// kernel-to-kernel gaps are already hidden and it measured no gain (34.1 vs 34.3 ms in round 1), so "auto" leaves captures alone.
+bool pdl_enabled(cudaStream_t stream) {
+  const int m = pdl_mode();
+  if (m != 2) return m == 1;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return st == cudaStreamCaptureStatusNone;
 }
 
 static thread_local bool g_trace_on = false;

@@ -77,15 +77,15 @@ static inline void trace_op(const char* name, A... a) {
   } while (0)
 
 // ---- programmatic dependent launch ---------------------------------------------------------------
-// With S2M2_PDL=1 every kernel is launched with the programmatic-stream-serialization attribute; each kernel runs
-// pdl_sync() before it touches global memory, so its CTAs may be scheduled (and run their shared-memory / TMEM / barrier
-// prologue) while the last wave of the previous kernel drains, then block until that kernel has completed and its writes
-// are visible.  Without the attribute (the default) both instructions are no-ops.
+// Kernels launched with the programmatic-stream-serialization attribute (S2M2_PDL: 0 never, 1 always, default auto = eager
+// launches yes, launches under stream capture no; api.cu) may start while the last wave of the previous kernel drains: each kernel
+// runs pdl_sync() before it touches global memory, so its CTAs run their shared-memory / TMEM / barrier prologue early, then block
+// until that kernel has completed and its writes are visible.  Without the attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-bool pdl_enabled();
+bool pdl_enabled(cudaStream_t stream);
 
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -99,7 +99,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(stream) ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError() in S2M2_LAUNCH_OK
 }
 

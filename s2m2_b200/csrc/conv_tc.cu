@@ -890,7 +890,7 @@ static int launch_tc2(const TcMaps& maps, const TcP& p, int m_tiles, int n_tiles
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = pdl_enabled(s) ? 2 : 1;
     if (!plan_mode()) (void)cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, STAGES, PAIR, BRES>, maps, p, m_tiles, n_tiles);
     S2M2_LAUNCH_OK("conv_tc_pair");
     return 0;

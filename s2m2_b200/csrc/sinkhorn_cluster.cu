@@ -409,7 +409,7 @@ int sinkhorn_cluster_launch(const float* cv, int B, int h, int w, float* disp, f
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_enabled(s) ? 2 : 1;
   if (!plan_mode()) (void)cudaLaunchKernelEx(&cfg, kernel, p);
   S2M2_LAUNCH_OK("sinkhorn_cluster");
   return 0;
