@@ -576,7 +576,14 @@ struct Blk {
   Arena* a;
   size_t off, bytes;
   Blk(Arena* aa, size_t o, size_t b) : a(aa), off(o), bytes(b) {}
-  ~Blk() { a->release(off, bytes); }
+  ~Blk() {
+    if (trace_on()) {
+      char t[64];
+      snprintf(t, sizeof(t), "free %p", (void*)(a->base + off));
+      trace_append(t);
+    }
+    a->release(off, bytes);
+  }
 };
 struct T {   // strided-NHWC view (ops.tview): channels contiguous, pixels ld elements apart
   char* p = nullptr;

@@ -158,6 +158,33 @@ def canonical(trace: str):
             serial += 1
         elif parts and parts[0] == "static":
             add(int(parts[2], 16), int(parts[3]), parts[1])
+        elif parts and parts[0] == "free":
+            pass                                   # lifetimes: only the C++ arena reports them (check_arena below)
         else:
             out.append(_PTR.sub(name_of, line))
     return out
+
+
+def check_arena(trace: str, base: int, need: int):
+    """The C++ host's workspace arena, from its raw trace: every block inside [base, base + need), and no two LIVE blocks overlap
+    (``alloc`` / ``free`` lines; blocks outside the arena's address range — the caller's output buffer — are ignored)."""
+    live = {}
+    peak = 0
+    for line in trace.splitlines():
+        p = line.split()
+        if not p:
+            continue
+        if p[0] == "alloc":
+            a, n = int(p[1], 16), max(int(p[2]), 1)
+            if not (base <= a < base + (1 << 44)):
+                continue
+            assert a + n <= base + need, f"block {a - base}+{n} beyond the planned workspace {need}"
+            for b, m in live.items():
+                assert a + n <= b or b + m <= a, f"live blocks overlap: {a - base}+{n} and {b - base}+{m}"
+            live[a] = n
+            peak = max(peak, a + n - base)
+        elif p[0] == "free":
+            assert int(p[1], 16) in live, "free of an unknown block"
+            del live[int(p[1], 16)]
+    assert not live, f"{len(live)} blocks never released"
+    return peak
