@@ -197,16 +197,20 @@ def main():
     C, NTR = MODEL_TABLE[args.model]
     dist = None
     bcast_bytes = 0
+    nccl_log = None
     if world > 1:
         import datetime
         import torch.distributed as dist
-        # evidence of the communicator: NCCL's own init log (the "rank r nranks N ... Init COMPLETE" lines), sent to stderr so that
-        # stdout stays the one JSON line.  A quieter preset (unset / VERSION / WARN) is raised to INFO; INFO / TRACE / a log file
-        # chosen by the caller are left alone.
+        # evidence of the communicator: NCCL's own init log (the "rank r nranks N ... Init COMPLETE" lines).  It goes to a per-rank
+        # file and its communicator lines are re-emitted on this rank's stderr after the broadcast, so that stdout stays the one JSON
+        # line and ranks do not overwrite each other when stderr is a file (NCCL opens its log file truncating).  A quieter preset
+        # (unset / VERSION / WARN) is raised to INFO; INFO / TRACE / a log file chosen by the caller are left alone.
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            nccl_log = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"s2m2_bench_nccl_rank{rank}_{os.getpid()}.log")
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
 
     model = S2M2(C, 1, NTR, use_positivity=True, refine_iter=3, precision=args.precision).eval()
@@ -221,6 +225,16 @@ def main():
         bcast_bytes = broadcast_packed(model, dev, 0)
         torch.cuda.synchronize()
         print(f"[rank {rank}/{world}] packed weights received: {bcast_bytes / 1e6:.1f} MB (one NCCL broadcast from rank 0)", file=sys.stderr, flush=True)
+        if nccl_log and os.path.exists(nccl_log):
+            import re
+            with open(nccl_log, errors="replace") as f:
+                keep = [ln.rstrip() for ln in f if re.search(r"Init COMPLETE|nranks|NVLS|NCCL version", ln)]
+            for ln in keep[:12]:
+                print(f"[rank {rank}/{world}] {ln}", file=sys.stderr, flush=True)
+            try:
+                os.remove(nccl_log)
+            except OSError:
+                pass
 
     left_h, right_h = synthetic_pair(B, H, W, 1 + rank)
     left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
